@@ -1,0 +1,184 @@
+/* sb200.h -- C ABI of libsb200.so: the B200-native (sm_100a) implementation of SparseBase's
+ * data-parallel preprocessing hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces the arithmetic of one function
+ * of the reference (sparcityeu/SparseBase v0.3.1; paths relative to src/sparsebase/) and is
+ * what the reference-side shim (sparsebase_b200/host/) binds:
+ *
+ *   sb200_coo_sort            format/coo.cc:96-157          COO ctor: sortedness check + (row,col) sort
+ *   sb200_coo_to_csr          converter/converter_order_two.cc:162-212 (CooCsrFunctionConditional)
+ *   sb200_csr_to_coo          converter/converter_order_two.cc:71-118  (CsrCooFunctionConditional)
+ *   sb200_coo_to_csc          converter/converter_order_two.cc:20-70   (CooCscFunctionConditional)
+ *   sb200_csr_to_csc          converter/converter_order_two.cc:119-128 (CsrCscFunctionConditional)
+ *   sb200_compressed_sort     format/csr.cc:99-157, format/csc.cc:99-157  CSR/CSC ctor check + segment sort
+ *   sb200_degree_reorder      reorder/degree_reorder.cc:22-62  (DegreeReorder::CalculateReorderCSR)
+ *   sb200_rcm_reorder         reorder/rcm_reorder.cc:22-166    (RCMReorder::peripheral + GetReorderCSR)
+ *   sb200_permute2d           permute/permute_order_two.cc:21-79 (PermuteOrderTwo::PermuteOrderTwoCSR)
+ *   sb200_permute1d           permute/permute_order_one.cc:17-37 (PermuteOrderOne::PermuteArray)
+ *   sb200_inverse_permutation bases/reorder_base.h:662-671     (ReorderBase::InversePermutation)
+ *   sb200_degrees             feature/degrees.cc:93-105        (Degrees::GetDegreesCSR)
+ *   sb200_degree_distribution feature/degree_distribution.cc:146-162 (GetDegreeDistributionCSR)
+ *   sb200_malloc/free/memcpy_*  converter/converter_order_two_cuda.cu:11-105,
+ *                             converter/converter_order_one_cuda.cu:10-43, utils/utils_cuda.cuh:6-9
+ *   sb200_can_access_peer     converter/converter_cuda.cu:12-21 (CUDAPeerToPeer)
+ *   sb200_device_count        context/cuda_context_cuda.cu:9-15 (CUDAContext ctor validation)
+ *   sb200_partition_rows      (new) nnz-balanced contiguous row blocks for the multi-GPU path
+ *
+ * Conventions
+ *  - Plain C: pointers and sizes only, no C++/torch types.  Every function returns 0 on
+ *    success or an SB200_ERR_* code and never throws; sb200_last_error() returns a
+ *    thread-local message for the last failure.
+ *  - Unless a parameter is prefixed h_, array pointers are DEVICE pointers on `device`.
+ *    Outputs are caller-allocated (sb200_malloc or any cudaMalloc-compatible allocator, so
+ *    they can be owned by a CUDACSR / CUDAArray with the reference's CUDADeleter = cudaFree).
+ *  - Element types are given as SB200_* dtype codes: id_type (IDType), nnz_type (NNZType),
+ *    val_type (ValueType; SB200_VOID or a NULL vals pointer means "no values").
+ *    Supported: id_type in {I32,U32,I64,U64}, nnz_type in {I32,U32,I64,U64} with
+ *    sizeof(nnz) >= sizeof(id), val_type any 4- or 8-byte type or VOID.  Values are moved
+ *    bit-exactly and never interpreted (except as a tie-break key, see sb200_compressed_sort).
+ *    Index values must be non-negative and below 2^31 (4-byte) / 2^62 (8-byte).
+ *  - `stream` is a cudaStream_t (NULL = the legacy default stream).  Calls are asynchronous
+ *    with respect to the host unless stated otherwise; scratch memory comes from the
+ *    stream-ordered CUDA memory pool of `device`.
+ *  - There is NO CPU fallback anywhere in this library: without a CUDA device every compute
+ *    entry point fails with SB200_ERR_CUDA.
+ */
+#ifndef SB200_H_
+#define SB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_ABI_VERSION 1
+
+enum sb200_dtype {
+  SB200_VOID = 0,
+  SB200_I32 = 1,
+  SB200_I64 = 2,
+  SB200_U32 = 3,
+  SB200_U64 = 4,
+  SB200_F32 = 5,
+  SB200_F64 = 6
+};
+
+enum sb200_error {
+  SB200_OK = 0,
+  SB200_ERR_CUDA = 1,        /* a CUDA runtime call failed (message has the cudaError string) */
+  SB200_ERR_BAD_DTYPE = 2,   /* unsupported dtype combination */
+  SB200_ERR_BAD_ARG = 3,     /* null pointer / negative size / size limit exceeded */
+  SB200_ERR_BAD_DEVICE = 4,  /* device id out of range (reference: utils::CUDADeviceException) */
+  SB200_ERR_ALLOC = 5,       /* allocation failed (reference: utils::AllocationException) */
+  SB200_ERR_INTERNAL = 6
+};
+
+int sb200_abi_version(void);
+const char *sb200_last_error(void);
+
+/* ---- contexts, memory and transfer (reference: CUDAContext, CUDACSR/CUDAArray transfer) ---- */
+int sb200_device_count(int *h_count);
+int sb200_can_access_peer(int device, int peer_device, int *h_can);
+int sb200_enable_peer_access(int device, int peer_device);
+int sb200_malloc(int device, size_t bytes, void **h_out_ptr);
+int sb200_free(int device, void *ptr);
+int sb200_malloc_host(size_t bytes, void **h_out_ptr); /* pinned host memory */
+int sb200_free_host(void *h_ptr);
+int sb200_memcpy_h2d(int device, void *dst, const void *h_src, size_t bytes, void *stream);
+int sb200_memcpy_d2h(int device, void *h_dst, const void *src, size_t bytes, void *stream);
+int sb200_memcpy_d2d(int dst_device, void *dst, int src_device, const void *src, size_t bytes,
+                     void *stream);
+int sb200_stream_synchronize(int device, void *stream);
+
+/* ---- format constructors ---- */
+
+/* COO constructor semantics (ignore_sort=false): if the (row,col) sequence has an inversion,
+ * sort row/col/vals IN PLACE by (row, col).  *h_was_sorted (optional, host) receives 1 when
+ * the input was already sorted.  Synchronises the stream (the check result steers the host). */
+int sb200_coo_sort(int device, int64_t n, int64_t m, int64_t nnz, void *row, void *col,
+                   void *vals, int id_type, int val_type, int *h_was_sorted, void *stream);
+
+/* CSR / CSC constructor semantics (ignore_sort=false) on a compressed layout ptr[n_seg+1],
+ * idx[nnz], vals[nnz]: if ANY segment is not non-decreasing, sort EVERY segment by
+ * (idx, value) in place.  *h_was_sorted as above.  Synchronises the stream. */
+int sb200_compressed_sort(int device, int64_t n_seg, int64_t n_idx, int64_t nnz, const void *ptr,
+                          void *idx, void *vals, int id_type, int nnz_type, int val_type,
+                          int *h_was_sorted, void *stream);
+
+/* ---- order-two conversions ---- */
+
+/* COO (constructed, i.e. (row,col)-sorted unless the caller used ignore_sort) -> CSR.
+ * out_row_ptr[n+1], out_col[nnz], out_vals[nnz].  Followed by the CSR-constructor check/sort. */
+int sb200_coo_to_csr(int device, int64_t n, int64_t m, int64_t nnz, const void *row,
+                     const void *col, const void *vals, void *out_row_ptr, void *out_col,
+                     void *out_vals, int id_type, int nnz_type, int val_type, void *stream);
+
+/* CSR -> COO: out_row[nnz] (row_ptr expanded), out_col, out_vals copied. */
+int sb200_csr_to_coo(int device, int64_t n, int64_t m, int64_t nnz, const void *row_ptr,
+                     const void *col, const void *vals, void *out_row, void *out_col,
+                     void *out_vals, int id_type, int nnz_type, int val_type, void *stream);
+
+/* COO -> CSC: out_col_ptr[n+1] (n = dims[0]: the reference's square assumption; columns
+ * >= n are not representable there, here col indices up to max(n,m)-1 are accepted and
+ * out_col_ptr must have max(n,m)+1 entries only if m > n ... see DESIGN.md), out_row[nnz]
+ * ascending within each column, out_vals[nnz]. */
+int sb200_coo_to_csc(int device, int64_t n, int64_t m, int64_t nnz, const void *row,
+                     const void *col, const void *vals, void *out_col_ptr, void *out_row,
+                     void *out_vals, int id_type, int nnz_type, int val_type, void *stream);
+
+/* CSR -> CSC (transpose of the layout): = csr_to_coo followed by coo_to_csc. */
+int sb200_csr_to_csc(int device, int64_t n, int64_t m, int64_t nnz, const void *row_ptr,
+                     const void *col, const void *vals, void *out_col_ptr, void *out_row,
+                     void *out_vals, int id_type, int nnz_type, int val_type, void *stream);
+
+/* ---- reorderings: out_inv[n] is the reference's result convention inv[old] = new ---- */
+int sb200_degree_reorder(int device, int64_t n, const void *row_ptr, int ascending,
+                         void *out_inv, int id_type, int nnz_type, void *stream);
+
+int sb200_rcm_reorder(int device, int64_t n, int64_t nnz, const void *row_ptr, const void *col,
+                      void *out_inv, int id_type, int nnz_type, void *stream);
+
+/* ---- applying a permutation ---- */
+
+/* row_order[n] / col_order[m] are inverse permutations (inv[old] = new); NULL = identity.
+ * out_row_ptr[n+1], out_col[nnz] (ascending within each row), out_vals[nnz]. */
+int sb200_permute2d(int device, int64_t n, int64_t m, int64_t nnz, const void *row_ptr,
+                    const void *col, const void *vals, const void *row_order,
+                    const void *col_order, void *out_row_ptr, void *out_col, void *out_vals,
+                    int id_type, int nnz_type, int val_type, void *stream);
+
+/* out[order[i]] = vals[i]  (== out[i] = vals[inverse(order)[i]]) */
+int sb200_permute1d(int device, int64_t len, const void *vals, const void *order, void *out,
+                    int id_type, int val_type, void *stream);
+
+/* out[perm[i]] = i */
+int sb200_inverse_permutation(int device, int64_t len, const void *perm, void *out, int id_type,
+                              void *stream);
+
+/* ---- degree features ---- */
+int sb200_degrees(int device, int64_t n, const void *row_ptr, void *out_degrees, int id_type,
+                  int nnz_type, void *stream);
+
+/* out_dist[i] = (row_ptr[i+1]-row_ptr[i]) / (FeatureType) nnz ; feature_type in {F32,F64} */
+int sb200_degree_distribution(int device, int64_t n, int64_t nnz, const void *row_ptr,
+                              void *out_dist, int nnz_type, int feature_type, void *stream);
+
+/* ---- multi-GPU sharding helper ---- */
+
+/* Split rows [0,n) into `parts` contiguous blocks with (nearly) equal nnz: h_bounds[parts+1]
+ * (host, int64) with bounds[0]=0, bounds[parts]=n and bounds[k] = the first row whose
+ * row_ptr >= k*nnz/parts.  Synchronises the stream. */
+int sb200_partition_rows(int device, int64_t n, int64_t nnz, const void *row_ptr, int nnz_type,
+                         int parts, int64_t *h_bounds, void *stream);
+
+/* Number of kernels launched by this library on the calling thread since the last reset
+ * (bench.py reports it as gpu_launches). */
+int64_t sb200_launch_count(void);
+void sb200_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SB200_H_ */

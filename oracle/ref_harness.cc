@@ -1,0 +1,312 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into, imported by or called from the
+// product path (sparsebase_b200/, include/).  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load what this builds.
+//
+// ref_harness.cc -- thin extern "C" harness around the UNMODIFIED reference
+// (sparcityeu/SparseBase, header-only mode).  It is compiled by oracle/Makefile
+// from the sources where they lie under /root/reference/src into
+// oracle/_ref/libsbref.so; no reference source is copied into this repo.
+//
+// Every entry point calls exactly the public reference API the examples use
+// (examples/format_conversion/format_conversion.cc:16-18,
+//  examples/degree_order/degree_order.cc:44-46, examples/rcm_order/rcm_order.cc:40-44):
+//   COO ctor                      src/sparsebase/format/coo.cc:76-158
+//   coo->Convert<CSR>             src/sparsebase/converter/converter_order_two.cc:162-212
+//   csr->Convert<CSC>             src/sparsebase/converter/converter_order_two.cc:119-128
+//   csr->Convert<COO>             src/sparsebase/converter/converter_order_two.cc:71-118
+//   coo->Convert<CSC>             src/sparsebase/converter/converter_order_two.cc:20-70
+//   CSR ctor (row sort)           src/sparsebase/format/csr.cc:78-159
+//   ReorderBase::Reorder<Degree>  src/sparsebase/reorder/degree_reorder.cc:22-62
+//   ReorderBase::Reorder<RCM>     src/sparsebase/reorder/rcm_reorder.cc:22-166
+//   ReorderBase::Permute2D        src/sparsebase/permute/permute_order_two.cc:21-79
+//   ReorderBase::Permute1D        src/sparsebase/permute/permute_order_one.cc:17-37
+//   ReorderBase::InversePermutation  src/sparsebase/bases/reorder_base.h:662-671
+//   Degrees / DegreeDistribution  src/sparsebase/feature/degrees.cc:93-105,
+//                                 src/sparsebase/feature/degree_distribution.cc:146-162
+//
+// Harness rules: the reference reads and writes mr[n], one element
+// past `new IDType[n]()`, in degree_reorder.cc:41-45 (heap overflow; it only "works" when the
+// block happens to be mmap'd with zeroed slack).  This library therefore replaces
+// operator new[] for its own code (linked with -Bsymbolic) by a zero-filled allocation with
+// 64 bytes of slack, which gives the stray slot the value 0 deterministically -- the same
+// result the reference produces whenever it does not crash.  Logger silenced; results are
+// copied into caller-owned buffers.
+#include <malloc.h>
+
+#include <cstdlib>
+#include <new>
+
+void *operator new[](std::size_t sz) {
+  void *p = std::calloc(1, sz + 64);
+  if (!p) throw std::bad_alloc();
+  return p;
+}
+void operator delete[](void *p) noexcept { std::free(p); }
+void operator delete[](void *p, std::size_t) noexcept { std::free(p); }
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "sparsebase/bases/reorder_base.h"
+#include "sparsebase/context/cpu_context.h"
+#include "sparsebase/feature/degree_distribution.h"
+#include "sparsebase/feature/degrees.h"
+#include "sparsebase/format/array.h"
+#include "sparsebase/format/coo.h"
+#include "sparsebase/format/csc.h"
+#include "sparsebase/format/csr.h"
+#include "sparsebase/reorder/degree_reorder.h"
+#include "sparsebase/reorder/rcm_reorder.h"
+#include "sparsebase/utils/logger.h"
+
+using namespace sparsebase;
+
+namespace {
+struct Init {
+  Init() {
+    utils::Logger::set_level(utils::LOG_LVL_NONE);
+  }
+} g_init;
+
+context::CPUContext g_cpu;
+
+template <typename T>
+void copy_out(T *dst, const T *src, size_t cnt) {
+  if constexpr (!std::is_same_v<T, void>) {
+    if (dst && src && cnt) std::memcpy(dst, src, cnt * sizeof(T));
+  }
+}
+
+// ---- COO constructor: sorted-check + in-place sort of the caller's arrays ----
+template <typename I, typename N, typename V>
+int coo_ctor_sort(int64_t n, int64_t m, int64_t nnz, I *row, I *col, V *vals) {
+  format::COO<I, N, V> coo((I)n, (I)m, (N)nnz, row, col, vals, format::kNotOwned);
+  return 0;
+}
+
+template <typename I, typename N, typename V>
+int coo_to_csr(int64_t n, int64_t m, int64_t nnz, I *row, I *col, V *vals,
+               N *o_row_ptr, I *o_col, V *o_vals) {
+  format::COO<I, N, V> coo((I)n, (I)m, (N)nnz, row, col, vals, format::kNotOwned);
+  auto *csr = coo.template Convert<format::CSR>(&g_cpu);
+  copy_out(o_row_ptr, csr->get_row_ptr(), (size_t)n + 1);
+  copy_out(o_col, csr->get_col(), (size_t)nnz);
+  copy_out(o_vals, csr->get_vals(), (size_t)nnz);
+  delete csr;
+  return 0;
+}
+
+template <typename I, typename N, typename V>
+int coo_to_csc(int64_t n, int64_t m, int64_t nnz, I *row, I *col, V *vals,
+               N *o_col_ptr, I *o_row, V *o_vals) {
+  format::COO<I, N, V> coo((I)n, (I)m, (N)nnz, row, col, vals, format::kNotOwned);
+  auto *csc = coo.template Convert<format::CSC>(&g_cpu);
+  copy_out(o_col_ptr, csc->get_col_ptr(), (size_t)n + 1);
+  copy_out(o_row, csc->get_row(), (size_t)nnz);
+  copy_out(o_vals, csc->get_vals(), (size_t)nnz);
+  delete csc;
+  return 0;
+}
+
+template <typename I, typename N, typename V>
+int csr_to_csc(int64_t n, int64_t m, N *row_ptr, I *col, V *vals, N *o_col_ptr,
+               I *o_row, V *o_vals) {
+  format::CSR<I, N, V> csr((I)n, (I)m, row_ptr, col, vals, format::kNotOwned);
+  int64_t nnz = (int64_t)csr.get_num_nnz();
+  auto *csc = csr.template Convert<format::CSC>(&g_cpu);
+  copy_out(o_col_ptr, csc->get_col_ptr(), (size_t)n + 1);
+  copy_out(o_row, csc->get_row(), (size_t)nnz);
+  copy_out(o_vals, csc->get_vals(), (size_t)nnz);
+  delete csc;
+  return 0;
+}
+
+template <typename I, typename N, typename V>
+int csr_to_coo(int64_t n, int64_t m, N *row_ptr, I *col, V *vals, I *o_row,
+               I *o_col, V *o_vals) {
+  format::CSR<I, N, V> csr((I)n, (I)m, row_ptr, col, vals, format::kNotOwned);
+  int64_t nnz = (int64_t)csr.get_num_nnz();
+  auto *coo = csr.template Convert<format::COO>(&g_cpu);
+  copy_out(o_row, coo->get_row(), (size_t)nnz);
+  copy_out(o_col, coo->get_col(), (size_t)nnz);
+  copy_out(o_vals, coo->get_vals(), (size_t)nnz);
+  delete coo;
+  return 0;
+}
+
+// ---- CSR constructor: sortedness check + per-row (col,val) sort, in place ----
+template <typename I, typename N, typename V>
+int csr_ctor_sort(int64_t n, int64_t m, N *row_ptr, I *col, V *vals) {
+  format::CSR<I, N, V> csr((I)n, (I)m, row_ptr, col, vals, format::kNotOwned);
+  return 0;
+}
+
+template <typename I, typename N, typename V>
+int degree_reorder(int64_t n, int64_t m, N *row_ptr, I *col, V *vals, int ascending,
+                   I *o_inv) {
+  format::CSR<I, N, V> csr((I)n, (I)m, row_ptr, col, vals, format::kNotOwned, true);
+  I *inv = bases::ReorderBase::Reorder<reorder::DegreeReorder>(
+      {ascending != 0}, &csr, {&g_cpu}, true);
+  copy_out(o_inv, inv, (size_t)n);
+  delete[] inv;
+  return 0;
+}
+
+template <typename I, typename N, typename V>
+int rcm_reorder(int64_t n, int64_t m, N *row_ptr, I *col, V *vals, I *o_inv) {
+  format::CSR<I, N, V> csr((I)n, (I)m, row_ptr, col, vals, format::kNotOwned, true);
+  I *inv = bases::ReorderBase::Reorder<reorder::RCMReorder>({}, &csr, {&g_cpu}, true);
+  copy_out(o_inv, inv, (size_t)n);
+  delete[] inv;
+  return 0;
+}
+
+// Two-order variant is what PermuteOrderTwo itself takes (row_order, col_order may be
+// null); ReorderBase::Permute2D passes the same array for both.
+template <typename I, typename N, typename V>
+int permute2d(int64_t n, int64_t m, N *row_ptr, I *col, V *vals, I *row_order,
+              I *col_order, N *o_row_ptr, I *o_col, V *o_vals) {
+  format::CSR<I, N, V> csr((I)n, (I)m, row_ptr, col, vals, format::kNotOwned, true);
+  int64_t nnz = (int64_t)csr.get_num_nnz();
+  format::CSR<I, N, V> *out;
+  // permute_order_two.cc:75 deletes an uninitialised pointer when row_order == nullptr:
+  // pass the identity order instead (same result by :53).
+  std::vector<I> identity;
+  if (row_order == nullptr) {
+    identity.resize((size_t)n);
+    for (int64_t i = 0; i < n; i++) identity[(size_t)i] = (I)i;
+    row_order = identity.data();
+  }
+  if (row_order == col_order && row_order != nullptr) {
+    out = bases::ReorderBase::Permute2D<format::CSR>(row_order, &csr, {&g_cpu}, true);
+  } else {
+    permute::PermuteOrderTwo<I, N, V> perm(row_order, col_order);
+    out = perm.GetPermutation(&csr, {&g_cpu}, true)->template As<format::CSR>();
+  }
+  copy_out(o_row_ptr, out->get_row_ptr(), (size_t)n + 1);
+  copy_out(o_col, out->get_col(), (size_t)nnz);
+  copy_out(o_vals, out->get_vals(), (size_t)nnz);
+  // result CSR is kNotOwned (permute_order_two.cc:76-77): free its arrays here
+  N *rp = out->get_row_ptr();
+  I *c = out->get_col();
+  V *v = out->get_vals();
+  delete out;
+  delete[] rp;
+  delete[] c;
+  if constexpr (!std::is_same_v<V, void>) delete[] v;
+  return 0;
+}
+
+template <typename I, typename V>
+int permute1d(int64_t len, V *vals, I *order, V *o_vals) {
+  format::Array<V> arr((format::DimensionType)len, vals, format::kNotOwned);
+  auto *out = bases::ReorderBase::Permute1D<format::Array>(order, &arr, {&g_cpu}, true);
+  copy_out(o_vals, out->get_vals(), (size_t)len);
+  delete out;
+  return 0;
+}
+
+template <typename I>
+int inverse_permutation(int64_t len, I *perm, I *o_inv) {
+  I *inv = bases::ReorderBase::InversePermutation(perm, (int64_t)len);
+  copy_out(o_inv, inv, (size_t)len);
+  delete[] inv;
+  return 0;
+}
+
+template <typename I, typename N, typename V>
+int degrees(int64_t n, int64_t m, N *row_ptr, I *col, V *vals, I *o_deg) {
+  format::CSR<I, N, V> csr((I)n, (I)m, row_ptr, col, vals, format::kNotOwned, true);
+  feature::Degrees<I, N, V> f;
+  I *d = f.GetDegrees(&csr, {&g_cpu}, true);
+  copy_out(o_deg, d, (size_t)n);
+  delete[] d;
+  return 0;
+}
+
+template <typename I, typename N, typename V, typename F>
+int degree_distribution(int64_t n, int64_t m, N *row_ptr, I *col, V *vals, F *o_dist) {
+  format::CSR<I, N, V> csr((I)n, (I)m, row_ptr, col, vals, format::kNotOwned, true);
+  feature::DegreeDistribution<I, N, V, F> f;
+  F *d = f.GetDistribution(&csr, {&g_cpu}, true);
+  copy_out(o_dist, d, (size_t)n);
+  delete[] d;
+  return 0;
+}
+}  // namespace
+
+// One block of extern "C" symbols per type triple.  TAG names IDType_NNZType_ValueType.
+#define SBREF_INSTANTIATE(TAG, I, N, V, F)                                                   \
+  extern "C" {                                                                               \
+  int sbref_coo_ctor_sort_##TAG(int64_t n, int64_t m, int64_t nnz, void *row, void *col,     \
+                                void *vals) {                                                \
+    return coo_ctor_sort<I, N, V>(n, m, nnz, (I *)row, (I *)col, (V *)vals);                 \
+  }                                                                                          \
+  int sbref_coo_to_csr_##TAG(int64_t n, int64_t m, int64_t nnz, void *row, void *col,        \
+                             void *vals, void *orp, void *oc, void *ov) {                    \
+    return coo_to_csr<I, N, V>(n, m, nnz, (I *)row, (I *)col, (V *)vals, (N *)orp, (I *)oc,  \
+                               (V *)ov);                                                     \
+  }                                                                                          \
+  int sbref_coo_to_csc_##TAG(int64_t n, int64_t m, int64_t nnz, void *row, void *col,        \
+                             void *vals, void *ocp, void *orow, void *ov) {                  \
+    return coo_to_csc<I, N, V>(n, m, nnz, (I *)row, (I *)col, (V *)vals, (N *)ocp,           \
+                               (I *)orow, (V *)ov);                                          \
+  }                                                                                          \
+  int sbref_csr_to_csc_##TAG(int64_t n, int64_t m, void *rp, void *col, void *vals,          \
+                             void *ocp, void *orow, void *ov) {                              \
+    return csr_to_csc<I, N, V>(n, m, (N *)rp, (I *)col, (V *)vals, (N *)ocp, (I *)orow,      \
+                               (V *)ov);                                                     \
+  }                                                                                          \
+  int sbref_csr_to_coo_##TAG(int64_t n, int64_t m, void *rp, void *col, void *vals,          \
+                             void *orow, void *oc, void *ov) {                               \
+    return csr_to_coo<I, N, V>(n, m, (N *)rp, (I *)col, (V *)vals, (I *)orow, (I *)oc,       \
+                               (V *)ov);                                                     \
+  }                                                                                          \
+  int sbref_csr_ctor_sort_##TAG(int64_t n, int64_t m, void *rp, void *col, void *vals) {     \
+    return csr_ctor_sort<I, N, V>(n, m, (N *)rp, (I *)col, (V *)vals);                       \
+  }                                                                                          \
+  int sbref_degree_reorder_##TAG(int64_t n, int64_t m, void *rp, void *col, void *vals,      \
+                                 int asc, void *oinv) {                                      \
+    return degree_reorder<I, N, V>(n, m, (N *)rp, (I *)col, (V *)vals, asc, (I *)oinv);      \
+  }                                                                                          \
+  int sbref_rcm_reorder_##TAG(int64_t n, int64_t m, void *rp, void *col, void *vals,         \
+                              void *oinv) {                                                  \
+    return rcm_reorder<I, N, V>(n, m, (N *)rp, (I *)col, (V *)vals, (I *)oinv);              \
+  }                                                                                          \
+  int sbref_permute2d_##TAG(int64_t n, int64_t m, void *rp, void *col, void *vals,           \
+                            void *ro, void *co, void *orp, void *oc, void *ov) {             \
+    return permute2d<I, N, V>(n, m, (N *)rp, (I *)col, (V *)vals, (I *)ro, (I *)co,          \
+                              (N *)orp, (I *)oc, (V *)ov);                                   \
+  }                                                                                          \
+  int sbref_degrees_##TAG(int64_t n, int64_t m, void *rp, void *col, void *vals,             \
+                          void *odeg) {                                                      \
+    return degrees<I, N, V>(n, m, (N *)rp, (I *)col, (V *)vals, (I *)odeg);                  \
+  }                                                                                          \
+  int sbref_degree_distribution_##TAG(int64_t n, int64_t m, void *rp, void *col,             \
+                                      void *vals, void *odist) {                             \
+    return degree_distribution<I, N, V, F>(n, m, (N *)rp, (I *)col, (V *)vals, (F *)odist);  \
+  }                                                                                          \
+  }
+
+SBREF_INSTANTIATE(i32_i32_f32, int32_t, int32_t, float, float)
+SBREF_INSTANTIATE(i32_i64_f32, int32_t, int64_t, float, float)
+SBREF_INSTANTIATE(i64_i64_f64, int64_t, int64_t, double, double)
+SBREF_INSTANTIATE(i32_i32_i32, int32_t, int32_t, int32_t, float)
+SBREF_INSTANTIATE(i32_i32_void, int32_t, int32_t, void, float)
+
+extern "C" {
+int sbref_permute1d_i32_f32(int64_t len, void *vals, void *order, void *out) {
+  return permute1d<int32_t, float>(len, (float *)vals, (int32_t *)order, (float *)out);
+}
+int sbref_permute1d_i64_f64(int64_t len, void *vals, void *order, void *out) {
+  return permute1d<int64_t, double>(len, (double *)vals, (int64_t *)order, (double *)out);
+}
+int sbref_inverse_permutation_i32(int64_t len, void *perm, void *out) {
+  return inverse_permutation<int32_t>(len, (int32_t *)perm, (int32_t *)out);
+}
+int sbref_inverse_permutation_i64(int64_t len, void *perm, void *out) {
+  return inverse_permutation<int64_t>(len, (int64_t *)perm, (int64_t *)out);
+}
+int sbref_abi_version() { return 1; }
+}

@@ -1,0 +1,233 @@
+"""ctypes binding of libsb200.so + thin torch-tensor wrappers.
+
+The wrappers take CUDA torch tensors (or raw device pointers), pass ``data_ptr()`` and the
+current torch stream to the C ABI and return freshly allocated CUDA tensors.  They mirror the
+reference's operator names (``coo_to_csr`` = ``COO::Convert<CSR>``, ``degree_reorder`` =
+``DegreeReorder::GetReorder`` ...).  No computation happens in Python.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsb200.so")
+
+VOID, I32, I64, U32, U64, F32, F64 = range(7)
+_DT = {torch.int32: I32, torch.int64: I64, torch.float32: F32, torch.float64: F64}
+
+# every symbol include/sb200.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "sb200_abi_version", "sb200_last_error", "sb200_device_count", "sb200_can_access_peer",
+    "sb200_enable_peer_access", "sb200_malloc", "sb200_free", "sb200_malloc_host",
+    "sb200_free_host", "sb200_memcpy_h2d", "sb200_memcpy_d2h", "sb200_memcpy_d2d",
+    "sb200_stream_synchronize", "sb200_coo_sort", "sb200_compressed_sort", "sb200_coo_to_csr",
+    "sb200_csr_to_coo", "sb200_coo_to_csc", "sb200_csr_to_csc", "sb200_degree_reorder",
+    "sb200_rcm_reorder", "sb200_permute2d", "sb200_permute1d", "sb200_inverse_permutation",
+    "sb200_degrees", "sb200_degree_distribution", "sb200_partition_rows", "sb200_launch_count",
+    "sb200_reset_launch_count",
+]
+
+
+class Sb200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libsb200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libsb200.so.  Fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m sparsebase_b200.build` "
+                "(there is no CPU fallback)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.sb200_last_error.restype = ctypes.c_char_p
+        _lib.sb200_launch_count.restype = ctypes.c_int64
+        _lib.sb200_reset_launch_count.restype = None
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise Sb200Error(rc, load().sb200_last_error().decode())
+
+
+def _p(t):
+    if t is None:
+        return ctypes.c_void_p(None)
+    if isinstance(t, int):
+        return ctypes.c_void_p(t)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _i64(x):
+    return ctypes.c_int64(int(x))
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(t):
+    assert t.is_cuda, "sparsebase_b200 operates on CUDA tensors only (no CPU fallback)"
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _vt(vals):
+    return VOID if vals is None else _DT[vals.dtype]
+
+
+def launch_count():
+    return int(load().sb200_launch_count())
+
+
+def reset_launch_count():
+    load().sb200_reset_launch_count()
+
+
+def device_count():
+    c = ctypes.c_int(0)
+    _check(load().sb200_device_count(ctypes.byref(c)))
+    return c.value
+
+
+# ------------------------------------------------------------------ format constructors
+def coo_sort_(n, m, row, col, vals=None):
+    """COO constructor semantics, in place.  Returns True when the input was already sorted."""
+    flag = ctypes.c_int(0)
+    _check(load().sb200_coo_sort(_dev(row), _i64(n), _i64(m), _i64(row.numel()), _p(row), _p(col),
+                                 _p(vals), _DT[row.dtype], _vt(vals), ctypes.byref(flag),
+                                 _stream()))
+    return bool(flag.value)
+
+
+def compressed_sort_(n_seg, n_idx, ptr, idx, vals=None):
+    """CSR/CSC constructor semantics (check + per-segment sort), in place."""
+    flag = ctypes.c_int(0)
+    _check(load().sb200_compressed_sort(_dev(idx), _i64(n_seg), _i64(n_idx), _i64(idx.numel()),
+                                        _p(ptr), _p(idx), _p(vals), _DT[idx.dtype],
+                                        _DT[ptr.dtype], _vt(vals), ctypes.byref(flag), _stream()))
+    return bool(flag.value)
+
+
+# ------------------------------------------------------------------ conversions
+def coo_to_csr(n, m, row, col, vals=None, nnz_dtype=torch.int32):
+    nnz = row.numel()
+    row_ptr = torch.empty(n + 1, dtype=nnz_dtype, device=row.device)
+    ocol = torch.empty_like(col)
+    ovals = None if vals is None else torch.empty_like(vals)
+    _check(load().sb200_coo_to_csr(_dev(row), _i64(n), _i64(m), _i64(nnz), _p(row), _p(col),
+                                   _p(vals), _p(row_ptr), _p(ocol), _p(ovals), _DT[row.dtype],
+                                   _DT[nnz_dtype], _vt(vals), _stream()))
+    return row_ptr, ocol, ovals
+
+
+def csr_to_coo(n, m, row_ptr, col, vals=None):
+    nnz = col.numel()
+    orow = torch.empty_like(col)
+    ocol = torch.empty_like(col)
+    ovals = None if vals is None else torch.empty_like(vals)
+    _check(load().sb200_csr_to_coo(_dev(col), _i64(n), _i64(m), _i64(nnz), _p(row_ptr), _p(col),
+                                   _p(vals), _p(orow), _p(ocol), _p(ovals), _DT[col.dtype],
+                                   _DT[row_ptr.dtype], _vt(vals), _stream()))
+    return orow, ocol, ovals
+
+
+def coo_to_csc(n, m, row, col, vals=None, nnz_dtype=torch.int32):
+    nnz = row.numel()
+    col_ptr = torch.empty(n + 1, dtype=nnz_dtype, device=row.device)
+    orow = torch.empty_like(row)
+    ovals = None if vals is None else torch.empty_like(vals)
+    _check(load().sb200_coo_to_csc(_dev(row), _i64(n), _i64(m), _i64(nnz), _p(row), _p(col),
+                                   _p(vals), _p(col_ptr), _p(orow), _p(ovals), _DT[row.dtype],
+                                   _DT[nnz_dtype], _vt(vals), _stream()))
+    return col_ptr, orow, ovals
+
+
+def csr_to_csc(n, m, row_ptr, col, vals=None, out=None):
+    nnz = col.numel()
+    if out is None:
+        col_ptr = torch.empty(n + 1, dtype=row_ptr.dtype, device=col.device)
+        orow = torch.empty_like(col)
+        ovals = None if vals is None else torch.empty_like(vals)
+    else:
+        col_ptr, orow, ovals = out
+    _check(load().sb200_csr_to_csc(_dev(col), _i64(n), _i64(m), _i64(nnz), _p(row_ptr), _p(col),
+                                   _p(vals), _p(col_ptr), _p(orow), _p(ovals), _DT[col.dtype],
+                                   _DT[row_ptr.dtype], _vt(vals), _stream()))
+    return col_ptr, orow, ovals
+
+
+# ------------------------------------------------------------------ reorderings
+def degree_reorder(n, row_ptr, ascending=True, id_dtype=torch.int32):
+    inv = torch.empty(n, dtype=id_dtype, device=row_ptr.device)
+    _check(load().sb200_degree_reorder(_dev(row_ptr), _i64(n), _p(row_ptr),
+                                       ctypes.c_int(1 if ascending else 0), _p(inv),
+                                       _DT[id_dtype], _DT[row_ptr.dtype], _stream()))
+    return inv
+
+
+def rcm_reorder(n, row_ptr, col):
+    inv = torch.empty(n, dtype=col.dtype, device=col.device)
+    _check(load().sb200_rcm_reorder(_dev(col), _i64(n), _i64(col.numel()), _p(row_ptr), _p(col),
+                                    _p(inv), _DT[col.dtype], _DT[row_ptr.dtype], _stream()))
+    return inv
+
+
+# ------------------------------------------------------------------ permutation
+def permute2d(n, m, row_ptr, col, vals, row_order, col_order, out=None):
+    nnz = col.numel()
+    if out is None:
+        orp = torch.empty_like(row_ptr)
+        ocol = torch.empty_like(col)
+        ovals = None if vals is None else torch.empty_like(vals)
+    else:
+        orp, ocol, ovals = out
+    _check(load().sb200_permute2d(_dev(col), _i64(n), _i64(m), _i64(nnz), _p(row_ptr), _p(col),
+                                  _p(vals), _p(row_order), _p(col_order), _p(orp), _p(ocol),
+                                  _p(ovals), _DT[col.dtype], _DT[row_ptr.dtype], _vt(vals),
+                                  _stream()))
+    return orp, ocol, ovals
+
+
+def permute1d(vals, order):
+    out = torch.empty_like(vals)
+    _check(load().sb200_permute1d(_dev(vals), _i64(vals.numel()), _p(vals), _p(order), _p(out),
+                                  _DT[order.dtype], _DT[vals.dtype], _stream()))
+    return out
+
+
+def inverse_permutation(perm):
+    out = torch.empty_like(perm)
+    _check(load().sb200_inverse_permutation(_dev(perm), _i64(perm.numel()), _p(perm), _p(out),
+                                            _DT[perm.dtype], _stream()))
+    return out
+
+
+# ------------------------------------------------------------------ features
+def degrees(n, row_ptr, id_dtype=torch.int32):
+    out = torch.empty(n, dtype=id_dtype, device=row_ptr.device)
+    _check(load().sb200_degrees(_dev(row_ptr), _i64(n), _p(row_ptr), _p(out), _DT[id_dtype],
+                                _DT[row_ptr.dtype], _stream()))
+    return out
+
+
+def degree_distribution(n, nnz, row_ptr, feature_dtype=torch.float32):
+    out = torch.empty(n, dtype=feature_dtype, device=row_ptr.device)
+    _check(load().sb200_degree_distribution(_dev(row_ptr), _i64(n), _i64(nnz), _p(row_ptr),
+                                            _p(out), _DT[row_ptr.dtype], _DT[feature_dtype],
+                                            _stream()))
+    return out
+
+
+def partition_rows(n, nnz, row_ptr, parts):
+    bounds = (ctypes.c_int64 * (parts + 1))()
+    _check(load().sb200_partition_rows(_dev(row_ptr), _i64(n), _i64(nnz), _p(row_ptr),
+                                       _DT[row_ptr.dtype], ctypes.c_int(parts), bounds, _stream()))
+    return list(bounds)
