@@ -120,10 +120,10 @@ int sb200_csr_to_coo(int device, int64_t n, int64_t m, int64_t nnz, const void *
                      const void *col, const void *vals, void *out_row, void *out_col,
                      void *out_vals, int id_type, int nnz_type, int val_type, void *stream);
 
-/* COO -> CSC: out_col_ptr[n+1] (n = dims[0]: the reference's square assumption; columns
- * >= n are not representable there, here col indices up to max(n,m)-1 are accepted and
- * out_col_ptr must have max(n,m)+1 entries only if m > n ... see DESIGN.md), out_row[nnz]
- * ascending within each column, out_vals[nnz]. */
+/* COO -> CSC: out_col_ptr[n+1] -- n = dims[0] entries, exactly like the reference
+ * (converter_order_two.cc:32 sizes col_ptr with the ROW count; m > n is undefined behaviour
+ * there and SB200_ERR_BAD_ARG here), out_row[nnz] ascending within each column,
+ * out_vals[nnz]. */
 int sb200_coo_to_csc(int device, int64_t n, int64_t m, int64_t nnz, const void *row,
                      const void *col, const void *vals, void *out_col_ptr, void *out_row,
                      void *out_vals, int id_type, int nnz_type, int val_type, void *stream);
@@ -139,6 +139,11 @@ int sb200_degree_reorder(int device, int64_t n, const void *row_ptr, int ascendi
 
 int sb200_rcm_reorder(int device, int64_t n, int64_t nnz, const void *row_ptr, const void *col,
                       void *out_inv, int id_type, int nnz_type, void *stream);
+
+/* Diagnostics of the last sb200_rcm_reorder call made by the calling thread:
+ * h_out4 = {levels walked by the persistent single-CTA kernel, levels done with grid-wide
+ * kernels, number of BFS traversals, number of non-trivial connected components}. */
+int sb200_rcm_last_stats(int64_t *h_out4);
 
 /* ---- applying a permutation ---- */
 
