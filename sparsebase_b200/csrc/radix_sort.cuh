@@ -45,11 +45,15 @@ struct RsChunking {
 };
 
 // ------------------------------------------------------------------ upsweep
+// Histogram of one digit over a chunk.  Keys are read with 16-byte vector loads, four per
+// thread in flight (64 B/thread, ~64 KB/SM at 1024 resident threads) -- enough bytes in flight
+// to cover the HBM bandwidth-delay product.
 template <typename K>
 __global__ void __launch_bounds__(kRsBlock)
     rs_upsweep_kernel(const K *__restrict__ keys, RsChunking ch, int shift, int bits,
                       int64_t *__restrict__ spine) {
   __shared__ unsigned hist[kRsWarps][kRsMaxBins];
+  constexpr int kVec = 16 / sizeof(K);  // keys per 16-byte load
   const unsigned wid = threadIdx.x >> 5;
   const unsigned mask = (1u << bits) - 1u;
   for (int i = threadIdx.x; i < kRsWarps * kRsMaxBins; i += kRsBlock) (&hist[0][0])[i] = 0;
@@ -58,7 +62,31 @@ __global__ void __launch_bounds__(kRsBlock)
   const int64_t begin = ch.tile_begin(c) * kRsTile;
   int64_t end = ch.tile_end(c) * kRsTile;
   if (end > ch.n) end = ch.n;
-  for (int64_t base = begin; base < end; base += (int64_t)kRsBlock * 4) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
+  int64_t base = begin;
+  if (aligned) {
+    const int64_t step = (int64_t)kRsBlock * kVec * 4;
+    for (; base + step <= end; base += step) {
+      uint4 q[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        q[k] = __ldcs(reinterpret_cast<const uint4 *>(keys + base) + k * kRsBlock + threadIdx.x);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if constexpr (sizeof(K) == 4) {
+          atomicAdd(&hist[wid][rs_digit<K>(q[k].x, shift, mask)], 1u);
+          atomicAdd(&hist[wid][rs_digit<K>(q[k].y, shift, mask)], 1u);
+          atomicAdd(&hist[wid][rs_digit<K>(q[k].z, shift, mask)], 1u);
+          atomicAdd(&hist[wid][rs_digit<K>(q[k].w, shift, mask)], 1u);
+        } else {
+          const K k0 = ((K)q[k].y << 32) | q[k].x, k1 = ((K)q[k].w << 32) | q[k].z;
+          atomicAdd(&hist[wid][rs_digit<K>(k0, shift, mask)], 1u);
+          atomicAdd(&hist[wid][rs_digit<K>(k1, shift, mask)], 1u);
+        }
+      }
+    }
+  }
+  for (; base < end; base += (int64_t)kRsBlock * 4) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       int64_t i = base + k * kRsBlock + threadIdx.x;
@@ -87,17 +115,22 @@ struct RsSmem {
 };
 
 template <typename T>
-__device__ __forceinline__ void rs_move_payload(const T *__restrict__ in, T *__restrict__ out,
-                                                RsSmem &s, int64_t warp_base, int64_t n,
-                                                const unsigned (&lp)[kRsIpt], int tile_count) {
-  T *stage = reinterpret_cast<T *>(s.stage);
+__device__ __forceinline__ void rs_load_payload(const T *__restrict__ in, int64_t warp_base,
+                                                int64_t n, T (&v)[kRsIpt]) {
   const unsigned lane = lane_id();
-  T v[kRsIpt];
 #pragma unroll
   for (int r = 0; r < kRsIpt; r++) {
     int64_t i = warp_base + r * 32 + lane;
     if (i < n) v[r] = ld_stream(in + i);
   }
+}
+
+template <typename T>
+__device__ __forceinline__ void rs_store_payload(const T (&v)[kRsIpt], T *__restrict__ out,
+                                                 RsSmem &s, int64_t warp_base, int64_t n,
+                                                 const unsigned (&lp)[kRsIpt], int tile_count) {
+  T *stage = reinterpret_cast<T *>(s.stage);
+  const unsigned lane = lane_id();
 #pragma unroll
   for (int r = 0; r < kRsIpt; r++) {
     int64_t i = warp_base + r * 32 + lane;
@@ -137,12 +170,18 @@ __global__ void __launch_bounds__(kRsBlock, 2)
 
     for (int i = threadIdx.x; i < kRsWarps * kRsMaxBins; i += kRsBlock) (&s.cnt[0][0])[i] = 0;
 
+    // all global loads of the tile are issued up front (keys and both payloads): one memory
+    // round trip per tile, 16 x (sizeof key + payloads) bytes in flight per thread
     K key[kRsIpt];
 #pragma unroll
     for (int r = 0; r < kRsIpt; r++) {
       int64_t i = warp_base + r * 32 + lane;
       key[r] = i < n ? ld_stream(kin + i) : K(0);
     }
+    [[maybe_unused]] typename std::conditional<has_val<V1>, V1, char>::type p1[kRsIpt];
+    [[maybe_unused]] typename std::conditional<has_val<V2>, V2, char>::type p2[kRsIpt];
+    if constexpr (has_val<V1>) rs_load_payload<V1>(v1in, warp_base, n, p1);
+    if constexpr (has_val<V2>) rs_load_payload<V2>(v2in, warp_base, n, p2);
     __syncthreads();  // counters zeroed
 
     // ---- stable ranking inside the warp: rounds in order, lanes in order ----
@@ -203,8 +242,8 @@ __global__ void __launch_bounds__(kRsBlock, 2)
       if (j < tile_count) kout[s.delta[s.sdig[j]] + j] = stage_k[j];
     }
     __syncthreads();
-    if constexpr (has_val<V1>) rs_move_payload<V1>(v1in, v1out, s, warp_base, n, lp, tile_count);
-    if constexpr (has_val<V2>) rs_move_payload<V2>(v2in, v2out, s, warp_base, n, lp, tile_count);
+    if constexpr (has_val<V1>) rs_store_payload<V1>(p1, v1out, s, warp_base, n, lp, tile_count);
+    if constexpr (has_val<V2>) rs_store_payload<V2>(p2, v2out, s, warp_base, n, lp, tile_count);
   }
 }
 

@@ -29,7 +29,6 @@ namespace sb200 {
 constexpr unsigned kUnvisited = 0xffffffffu;
 constexpr int kNwBlock = 1024;
 constexpr int kNwWarps = kNwBlock / 32;
-constexpr int kNwECap = 1 << 16;    // max expansion slots of a level handled by the narrow CTA
 constexpr int kNwGroupCap = 96;     // max degree in a CM frontier (bounds sibling groups)
 constexpr int64_t kBulkThreshold = 1 << 15;  // resets / inversions larger than this go wide
 
@@ -60,8 +59,14 @@ struct RcmState {
   int32_t status;
   int32_t next_phase_after_reset;
   int32_t pad;
+  int64_t frontier_maxdeg;  // max degree over the current frontier (for the narrow caps)
+  int64_t inv_qst, inv_end;  // pending bulk inversion
   int64_t stat_levels_narrow, stat_levels_wide, stat_bfs, stat_components;
 };
+
+__device__ __forceinline__ int bits_for_dev(unsigned long long v) {
+  return v ? 64 - __clzll((long long)v) : 0;
+}
 
 template <typename I, typename N>
 struct RcmArgs {
@@ -104,224 +109,288 @@ __device__ __forceinline__ void warp_expand(int64_t xs, unsigned d, Fn &&f) {
 }
 
 // ------------------------------------------------------------------------------------
-// NARROW regime
+// NARROW regime: one thread-block CLUSTER walks the levels.
+//
+// A single SM cannot issue the ~3 scattered L2 accesses per edge of a 4096-wide level fast
+// enough (measured: 36 us per level, LSU-bound), so the level is split over the CTAs of one
+// cluster (16 where the device allows it, else 8): CTA k owns the k-th contiguous share of the
+// frontier, claims with atomicMin in L2, and the CTAs exchange their counts through
+// distributed shared memory; cluster barriers (~0.2 us) replace grid-wide ones.
+// All CTAs run the same state machine on replicated state, so control flow is uniform.
 // ------------------------------------------------------------------------------------
-template <typename I>
-struct NwCaps {
-  static constexpr int kF = sizeof(I) == 4 ? 5120 : 4096;  // frontier / candidate capacity
-};
+constexpr int kClMax = 16;
+constexpr int kFl = 1024;  // frontier vertices per CTA and level
+constexpr int kEl = 4096;  // expansion slots per CTA and level (<= 4 per thread)
+constexpr int kClSpt = kEl / kNwBlock;
 
 template <typename I>
-struct NwSmem {
-  static constexpr int kF = NwCaps<I>::kF;
-  I F[kF];          // frontier vertices
-  int64_t Fx[kF];   // xadj[F[i]]
-  unsigned Fd[kF];  // degree of F[i]
-  unsigned off[kF + 1];
-  I cv[kF];         // candidates: vertex
-  unsigned ci[kF];  // parent position in the frontier
-  unsigned cd[kF];  // degree
-  int64_t cx[kF];   // xadj[cv]
+struct ClSmem {
+  I F[kFl];
+  int64_t Fx[kFl];
+  unsigned Fd[kFl];
+  unsigned off[kFl + 1];
+  I cv[kEl];
+  unsigned ci[kEl];
+  unsigned cd[kEl];
+  int64_t cx[kEl];
+  unsigned long long xch[2][kClMax][4];
+  unsigned long long mine[4];
   unsigned wtot[kNwWarps + 2];
   unsigned scratch[34];
   unsigned long long red[kNwWarps];
   RcmState S;
-  int in_smem;
-  int c_total;
-  int flag;
 };
 
-template <typename I, typename N>
-__device__ void nw_load_frontier(const RcmArgs<I, N> &a, NwSmem<I> &s, const I *queue) {
-  const int f = (int)(s.S.lvl_end - s.S.lvl_begin);
-  for (int i = threadIdx.x; i < f; i += kNwBlock) {
-    const I v = queue[s.S.lvl_begin + i];
+template <typename I>
+struct ClCursor {
+  int i;
+  unsigned j, rem;
+  int64_t p;
+  __device__ __forceinline__ void seek(const ClSmem<I> &s, int f, unsigned slot) {
+    int lo = 0, hi = f;  // last i with off[i] <= slot (its degree is non-zero)
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s.off[mid] <= slot)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    i = lo;
+    j = slot - s.off[lo];
+    rem = s.Fd[lo] - j;
+    p = s.Fx[lo] + j;
+  }
+  __device__ __forceinline__ void next(const ClSmem<I> &s, int f) {
+    p++;
+    j++;
+    if (--rem == 0) {
+      do {
+        i++;
+      } while (i < f && s.Fd[i] == 0);
+      if (i < f) {
+        rem = s.Fd[i];
+        p = s.Fx[i];
+        j = 0;
+      }
+    }
+  }
+};
+
+}  // namespace sb200
+#include <cooperative_groups.h>
+namespace sb200 {
+namespace cg = cooperative_groups;
+
+// Every CTA contributes s.mine[0..3]; afterwards s.xch[par][k][*] holds CTA k's values in every
+// CTA.  Contains a cluster barrier.  `par` alternates so that a fast CTA never overwrites
+// values a slow CTA has not read yet.
+template <typename I>
+__device__ __forceinline__ void cl_exchange(cg::cluster_group &cluster, ClSmem<I> &s, int &par) {
+  __syncthreads();
+  const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
+  if (threadIdx.x < C) {
+    unsigned long long *dst = cluster.map_shared_rank(&s.xch[par][rank][0], threadIdx.x);
+    dst[0] = s.mine[0];
+    dst[1] = s.mine[1];
+    dst[2] = s.mine[2];
+    dst[3] = s.mine[3];
+  }
+  cluster.sync();
+  par ^= 1;
+}
+
+// One BFS level across the cluster.  Returns the number of newly reached vertices (cluster
+// total), or -1 when the level has to be done by the wide path (nothing modified then).
+// On return *next_maxdeg holds the maximum degree among the new vertices.
+template <typename I, typename N, bool CM>
+__device__ long long cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a, ClSmem<I> &s,
+                              I *queue, int &par, unsigned cur_maxdeg, unsigned *next_maxdeg) {
+  const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
+  const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
+  const int64_t f = s.S.lvl_end - s.S.lvl_begin;
+  const int64_t fb = f * rank / C, fe = f * (rank + 1) / C;
+  const int fl = (int)(fe - fb);
+  // uniform feasibility checks (every CTA evaluates the same numbers)
+  const int64_t max_share = (f + C - 1) / C;
+  if (max_share > kFl) return -1;
+  if (CM && cur_maxdeg > (unsigned)kNwGroupCap) return -1;
+  const int jbits = bits_for_dev(cur_maxdeg);
+  if (!CM && bits_for_dev((unsigned long long)f) + jbits > 31) return -1;
+  const bool need_check = (unsigned long long)max_share * cur_maxdeg > (unsigned long long)kEl;
+
+  // ---- my share of the frontier: vertex, adjacency start, degree ----
+  for (int i = threadIdx.x; i < fl; i += kNwBlock) {
+    const I v = queue[s.S.lvl_begin + fb + i];
     const int64_t xs = (int64_t)a.xadj[v];
     s.F[i] = v;
     s.Fx[i] = xs;
     s.Fd[i] = (unsigned)((int64_t)a.xadj[v + 1] - xs);
   }
   __syncthreads();
-}
-
-// One BFS level in shared memory.  Returns the number of newly reached vertices, or -1 when
-// the level has to be done by the wide path (nothing has been modified in that case).
-template <typename I, typename N, bool CM>
-__device__ int nw_level(const RcmArgs<I, N> &a, NwSmem<I> &s, I *queue) {
-  constexpr int kF = NwSmem<I>::kF;
-  constexpr int kPer = (kF + kNwBlock - 1) / kNwBlock;
-  const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
-  const int f = (int)(s.S.lvl_end - s.S.lvl_begin);
-  if (!s.in_smem) nw_load_frontier(a, s, queue);
-
-  // ---- exclusive scan of the frontier degrees -> expansion slot offsets ----
-  unsigned local[kPer], sum = 0, mx = 0;
-#pragma unroll
-  for (int k = 0; k < kPer; k++) {
-    const int i = threadIdx.x * kPer + k;
-    local[k] = i < f ? s.Fd[i] : 0u;
-    sum += local[k];
-    mx = local[k] > mx ? local[k] : mx;
-  }
+  // exclusive scan of the degrees -> local expansion slot offsets
+  unsigned d = (int)threadIdx.x < fl ? s.Fd[threadIdx.x] : 0u;
   unsigned total;
-  unsigned run = block_exclusive_scan(sum, s.scratch, &total);
-  mx = warp_reduce_max(mx);
-  if (lane == 0) s.wtot[wid] = mx;
-#pragma unroll
-  for (int k = 0; k < kPer; k++) {
-    const int i = threadIdx.x * kPer + k;
-    if (i < f) s.off[i] = run;
-    run += local[k];
+  const unsigned ex = block_exclusive_scan(d, s.scratch, &total);
+  if ((int)threadIdx.x < fl) s.off[threadIdx.x] = ex;
+  __syncthreads();
+  if (need_check) {  // rare: agree cluster-wide that every share fits
+    if (threadIdx.x == 0) {
+      s.mine[0] = total;
+      s.mine[1] = s.mine[2] = s.mine[3] = 0;
+    }
+    cl_exchange(cluster, s, par);
+    unsigned long long mx = 0;
+    for (unsigned k = 0; k < C; k++) mx = s.xch[par ^ 1][k][0] > mx ? s.xch[par ^ 1][k][0] : mx;
+    if (mx > (unsigned long long)kEl) return -1;
   }
-  __syncthreads();
-  unsigned maxdeg = 0;
-  for (int w = 0; w < kNwWarps; w++) maxdeg = s.wtot[w] > maxdeg ? s.wtot[w] : maxdeg;
-  __syncthreads();
-  if (total > (unsigned)kNwECap || (CM && maxdeg > (unsigned)kNwGroupCap)) return -1;
 
-  // each warp owns a contiguous range of the frontier (keeps slot order inside the warp)
-  int vpw = (f + kNwWarps - 1) / kNwWarps;
-  vpw = (vpw + 31) & ~31;
-  const int wbeg = wid * vpw < f ? wid * vpw : f;
-  const int wend = wbeg + vpw < f ? wbeg + vpw : f;
+  const unsigned spt = (total + kNwBlock - 1) / kNwBlock;  // <= kClSpt
+  const unsigned s0 = threadIdx.x * spt;
+  const unsigned s1 = s0 + spt < total ? s0 + spt : total;
+  ClCursor<I> start;
+  start.i = 0;
+  start.j = 0;
+  start.rem = 0;
+  start.p = 0;
+  if (s0 < total) start.seek(s, fl, s0);
 
-  // ---- sweep 1: claims ----
-  for (int g = wbeg; g < wend; g += 32) {
-    const int i = g + lane;
-    const int64_t xs = i < wend ? s.Fx[i] : 0;
-    const unsigned d = i < wend ? s.Fd[i] : 0u;
-    const unsigned slot0 = s.off[g];
-    warp_expand(xs, d, [&](unsigned sl, unsigned j, int64_t p, bool valid) {
-      if (valid) {
-        const I v = a.adj[p];
-        const unsigned key = CM ? (unsigned)(g + j) + 1u : slot0 + sl + 1u;
-        atomicMin(&a.mark[v], key);
-      }
-    });
-  }
-  __syncthreads();
-
-  // ---- sweep 2: who won?  (winner bits of the first 64 rounds are kept in registers) ----
-  unsigned long long wbits = 0;
-  unsigned wcount = 0, round = 0;
-  for (int g = wbeg; g < wend; g += 32) {
-    const int i = g + lane;
-    const int64_t xs = i < wend ? s.Fx[i] : 0;
-    const unsigned d = i < wend ? s.Fd[i] : 0u;
-    const unsigned slot0 = s.off[g];
-    warp_expand(xs, d, [&](unsigned sl, unsigned j, int64_t p, bool valid) {
-      bool win = false;
-      if (valid) {
-        const I v = a.adj[p];
-        const unsigned key = CM ? (unsigned)(g + j) + 1u : slot0 + sl + 1u;
-        win = __ldcg(&a.mark[v]) == key;
-      }
-      wcount += __popc(__ballot_sync(0xffffffffu, win));
-      if (win && round < 64) wbits |= 1ull << round;
-      round++;
-    });
-  }
-  if (lane == 0) s.wtot[wid] = wcount;
-  __syncthreads();
-  if (wid == 0) {
-    const unsigned v = s.wtot[lane];
-    const unsigned inc = warp_inclusive_scan(v);
-    s.wtot[lane] = inc - v;
-    if (lane == 31) s.c_total = (int)inc;
-  }
-  __syncthreads();
-  const int c = s.c_total;
-  const bool overflow = c > kF;
-
-  // ---- sweep 3: ordered compaction of the winners (or roll the claims back) ----
+  // ---- sweep 1: claims.  key orders (global frontier position[, adjacency index]) ----
+  I v[kClSpt];
+  unsigned key[kClSpt];
+  unsigned prov = 0;  // slots that were the minimum when their claim landed
   {
-    unsigned pos = s.wtot[wid];
-    round = 0;
-    for (int g = wbeg; g < wend; g += 32) {
-      const int i = g + lane;
-      const int64_t xs = i < wend ? s.Fx[i] : 0;
-      const unsigned d = i < wend ? s.Fd[i] : 0u;
-      const unsigned slot0 = s.off[g];
-      warp_expand(xs, d, [&](unsigned sl, unsigned j, int64_t p, bool valid) {
-        bool win = false;
-        I v = 0;
-        if (valid) {
-          v = a.adj[p];
-          if (round < 64) {
-            win = (wbits >> round) & 1ull;
-          } else {
-            const unsigned key = CM ? (unsigned)(g + j) + 1u : slot0 + sl + 1u;
-            win = __ldcg(&a.mark[v]) == key;
-          }
+    ClCursor<I> cur = start;
+#pragma unroll
+    for (int u = 0; u < kClSpt; u++) {
+      if (s0 + u < s1) {
+        v[u] = a.adj[cur.p];
+        const unsigned gi = (unsigned)(fb + cur.i);
+        key[u] = CM ? gi + 1u : ((gi << jbits) | cur.j) + 1u;
+        cur.next(s, fl);
+      }
+    }
+    unsigned old[kClSpt];
+#pragma unroll
+    for (int u = 0; u < kClSpt; u++)
+      if (s0 + u < s1) old[u] = atomicMin(&a.mark[v[u]], key[u]);
+#pragma unroll
+    for (int u = 0; u < kClSpt; u++)
+      if (s0 + u < s1 && old[u] > key[u]) prov |= 1u << u;
+  }
+  cluster.sync();
+
+  // ---- sweep 2: which provisional winners survived? ----
+  unsigned wbits = 0, wcount = 0;
+  {
+    unsigned m[kClSpt];
+#pragma unroll
+    for (int u = 0; u < kClSpt; u++)
+      if ((prov >> u) & 1u) m[u] = __ldcg(&a.mark[v[u]]);
+#pragma unroll
+    for (int u = 0; u < kClSpt; u++) {
+      if (((prov >> u) & 1u) && m[u] == key[u]) {
+        wbits |= 1u << u;
+        wcount++;
+      }
+    }
+  }
+  unsigned c_local;
+  unsigned pos = block_exclusive_scan(wcount, s.scratch, &c_local);
+  // ---- ordered (slot order) compaction of my winners into shared memory ----
+  {
+    ClCursor<I> cur = start;
+#pragma unroll
+    for (int u = 0; u < kClSpt; u++) {
+      if (s0 + u < s1) {
+        if ((wbits >> u) & 1u) {
+          s.cv[pos] = v[u];
+          s.ci[pos] = (unsigned)cur.i;
+          pos++;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, win);
-        if (win) {
-          if (overflow) {
-            atomicExch(&a.mark[v], kUnvisited);  // undo: the wide path redoes this level
-          } else {
-            const unsigned k = pos + __popc(bal & lanemask_lt());
-            s.cv[k] = v;
-            s.ci[k] = (unsigned)(g + j);
-          }
-        }
-        pos += __popc(bal);
-        round++;
-      });
+        cur.next(s, fl);
+      }
     }
   }
   __syncthreads();
-  if (overflow) return -1;
 
   // ---- new vertices: mark visited, fetch their adjacency extent ----
+  const int c = (int)c_local;
+  unsigned mymax = 0;
   for (int k = threadIdx.x; k < c; k += kNwBlock) {
-    const I v = s.cv[k];
-    atomicExch(&a.mark[v], 0u);
-    const int64_t xs = (int64_t)a.xadj[v];
+    const I w = s.cv[k];
+    const int64_t xs = (int64_t)a.xadj[w];
+    const int64_t xe = (int64_t)a.xadj[w + 1];
+    atomicExch(&a.mark[w], 0u);
     s.cx[k] = xs;
-    s.cd[k] = (unsigned)((int64_t)a.xadj[v + 1] - xs);
+    const unsigned dg = (unsigned)(xe - xs);
+    s.cd[k] = dg;
+    mymax = dg > mymax ? dg : mymax;
   }
+  mymax = warp_reduce_max(mymax);
+  if (lane == 0) s.wtot[wid] = mymax;
   __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned mx = 0;
+    for (int w = 0; w < kNwWarps; w++) mx = s.wtot[w] > mx ? s.wtot[w] : mx;
+    s.mine[0] = c_local;
+    s.mine[1] = mx;
+    s.mine[2] = s.mine[3] = 0;
+  }
+  cl_exchange(cluster, s, par);
+  long long cbase = 0, ctotal = 0;
+  unsigned nmax = 0;
+  for (unsigned k = 0; k < C; k++) {
+    const long long ck = (long long)s.xch[par ^ 1][k][0];
+    if (k < rank) cbase += ck;
+    ctotal += ck;
+    const unsigned mk = (unsigned)s.xch[par ^ 1][k][1];
+    nmax = mk > nmax ? mk : nmax;
+  }
+  *next_maxdeg = nmax;
 
-  // ---- next frontier: slot order (peripheral) or (parent, degree, id) order (CM) ----
-  const int64_t out0 = s.S.lvl_end;
+  // ---- next frontier: slot order (peripheral) or (parent, degree, id) order (CM); the
+  //      sibling groups of a parent never leave the CTA that owns the parent ----
+  const int64_t out0 = s.S.lvl_end + cbase;
   for (int k = threadIdx.x; k < c; k += kNwBlock) {
-    int pos = k;
-    const I v = s.cv[k];
+    int dst = k;
+    const I w = s.cv[k];
     if (CM) {
-      const unsigned par = s.ci[k], dg = s.cd[k];
-      int rank = 0, left = 0;
-      for (int q = k - 1; q >= 0 && s.ci[q] == par; q--) {
+      const unsigned par_i = s.ci[k], dg = s.cd[k];
+      int rank_in = 0, left = 0;
+      for (int q = k - 1; q >= 0 && s.ci[q] == par_i; q--) {
         left++;
-        rank += (s.cd[q] < dg || (s.cd[q] == dg && s.cv[q] < v)) ? 1 : 0;
+        rank_in += (s.cd[q] < dg || (s.cd[q] == dg && s.cv[q] < w)) ? 1 : 0;
       }
-      for (int q = k + 1; q < c && s.ci[q] == par; q++)
-        rank += (s.cd[q] < dg || (s.cd[q] == dg && s.cv[q] < v)) ? 1 : 0;
-      pos = k - left + rank;
+      for (int q = k + 1; q < c && s.ci[q] == par_i; q++)
+        rank_in += (s.cd[q] < dg || (s.cd[q] == dg && s.cv[q] < w)) ? 1 : 0;
+      dst = k - left + rank_in;
     }
-    s.F[pos] = v;
-    s.Fx[pos] = s.cx[k];
-    s.Fd[pos] = s.cd[k];
-    queue[out0 + pos] = v;
+    queue[out0 + dst] = w;
+    // the next level starts by reading this vertex's adjacency list: pull it towards L2 now
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + s.cx[k]));
   }
-  __syncthreads();
-  return c;
+  cluster.sync();  // the queue slice is complete and visible to every CTA
+  return ctotal;
 }
 
 template <typename I, typename N>
 __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a) {
   extern __shared__ __align__(16) unsigned char nw_smem_raw[];
-  NwSmem<I> &s = *reinterpret_cast<NwSmem<I> *>(nw_smem_raw);
-  constexpr int kF = NwSmem<I>::kF;
+  ClSmem<I> &s = *reinterpret_cast<ClSmem<I> *>(nw_smem_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
   const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
+  int par = 0;
+  unsigned cur_maxdeg = 0;  // max degree over the current frontier (replicated)
   if (threadIdx.x == 0) {
     s.S = *a.state;
     s.S.status = ST_RUNNING;
-    s.in_smem = 0;
   }
   __syncthreads();
+  cur_maxdeg = (unsigned)s.S.frontier_maxdeg;
 
   for (;;) {
-    const int phase = s.S.phase;  // uniform: S is only written by thread 0 between barriers
+    const int phase = s.S.phase;  // replicated state: identical in every CTA
     if (phase == PH_DONE) {
       if (threadIdx.x == 0) s.S.status = ST_DONE;
       break;
@@ -330,7 +399,7 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
     // ================================================================ next component
     if (phase == PH_FIND) {
       // rcm_reorder.cc:104-116: scan for the next unvisited vertex; isolated vertices on the
-      // way are placed immediately, in index order.
+      // way are placed immediately, in index order.  CTA 0 scans, the result is broadcast.
       const int64_t base = s.S.next_i;
       if (base >= a.n || s.S.qwp >= a.n) {  // everything placed: nothing left to scan
         __syncthreads();
@@ -339,44 +408,51 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
         continue;
       }
       constexpr int kFindPer = 4;  // consecutive vertices per thread (keeps index order)
-      bool unvis[kFindPer], isolated[kFindPer];
-      unsigned stopper = 0xffffffffu;
+      if (rank == 0) {
+        bool unvis[kFindPer], isolated[kFindPer];
+        unsigned stopper = 0xffffffffu;
 #pragma unroll
-      for (int k = 0; k < kFindPer; k++) {
-        const int64_t i = base + (int64_t)threadIdx.x * kFindPer + k;
-        unvis[k] = false;
-        isolated[k] = false;
-        if (i < a.n) {
-          unvis[k] = __ldcg(&a.mark[i]) != 0u;
-          isolated[k] = a.xadj[i] == a.xadj[i + 1];
-        }
-      }
-#pragma unroll
-      for (int k = kFindPer - 1; k >= 0; k--)
-        if (unvis[k] && !isolated[k]) stopper = threadIdx.x * kFindPer + k;
-      // first unvisited, non-isolated vertex of this chunk
-      unsigned m = warp_reduce_min(stopper);
-      if (lane == 0) s.wtot[wid] = m;
-      __syncthreads();
-      m = 0xffffffffu;
-      for (int w = 0; w < kNwWarps; w++) m = s.wtot[w] < m ? s.wtot[w] : m;
-      unsigned take = 0;
-#pragma unroll
-      for (int k = 0; k < kFindPer; k++)
-        take += (unvis[k] && isolated[k] && threadIdx.x * kFindPer + k < m) ? 1u : 0u;
-      unsigned total;
-      unsigned off = block_exclusive_scan(take, s.scratch, &total);
-#pragma unroll
-      for (int k = 0; k < kFindPer; k++) {
-        if (unvis[k] && isolated[k] && threadIdx.x * kFindPer + k < m) {
+        for (int k = 0; k < kFindPer; k++) {
           const int64_t i = base + (int64_t)threadIdx.x * kFindPer + k;
-          const int64_t pos = s.S.qwp + off++;
-          a.Q[pos] = (I)i;
-          a.inv[i] = (I)pos;  // singleton component: reversed slice == itself
-          atomicExch(&a.mark[i], 0u);
+          unvis[k] = false;
+          isolated[k] = false;
+          if (i < a.n) {
+            unvis[k] = __ldcg(&a.mark[i]) != 0u;
+            isolated[k] = a.xadj[i] == a.xadj[i + 1];
+          }
+        }
+#pragma unroll
+        for (int k = kFindPer - 1; k >= 0; k--)
+          if (unvis[k] && !isolated[k]) stopper = threadIdx.x * kFindPer + k;
+        unsigned m = warp_reduce_min(stopper);
+        if (lane == 0) s.wtot[wid] = m;
+        __syncthreads();
+        m = 0xffffffffu;
+        for (int w = 0; w < kNwWarps; w++) m = s.wtot[w] < m ? s.wtot[w] : m;
+        unsigned take = 0;
+#pragma unroll
+        for (int k = 0; k < kFindPer; k++)
+          take += (unvis[k] && isolated[k] && threadIdx.x * kFindPer + k < m) ? 1u : 0u;
+        unsigned total;
+        unsigned off = block_exclusive_scan(take, s.scratch, &total);
+#pragma unroll
+        for (int k = 0; k < kFindPer; k++) {
+          if (unvis[k] && isolated[k] && threadIdx.x * kFindPer + k < m) {
+            const int64_t i = base + (int64_t)threadIdx.x * kFindPer + k;
+            const int64_t pos = s.S.qwp + off++;
+            a.Q[pos] = (I)i;
+            a.inv[i] = (I)pos;  // singleton component: reversed slice == itself
+            atomicExch(&a.mark[i], 0u);
+          }
+        }
+        if (threadIdx.x == 0) {
+          s.mine[0] = m;
+          s.mine[1] = total;
         }
       }
-      __syncthreads();
+      cl_exchange(cluster, s, par);
+      const unsigned m = (unsigned)s.xch[par ^ 1][0][0];
+      const unsigned total = (unsigned)s.xch[par ^ 1][0][1];
       if (threadIdx.x == 0) {
         s.S.qwp += total;
         if (m != 0xffffffffu) {
@@ -394,22 +470,29 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
       continue;
     }
 
-    // ================================================================ peripheral(): BFS start
-    if (phase == PH_PBFS_INIT) {  // rcm_reorder.cc:34-40
-      if (threadIdx.x == 0) {
-        const I r = (I)s.S.root;
-        s.S.rlevel = s.S.qlevel;
-        a.Qp[0] = r;
+    // ================================================================ BFS start
+    if (phase == PH_PBFS_INIT || phase == PH_CM_INIT) {  // rcm_reorder.cc:34-40 / :119-123
+      const bool cm = phase == PH_CM_INIT;
+      const I r = (I)s.S.root;
+      const int64_t at = cm ? s.S.qwp : 0;
+      if (rank == 0 && threadIdx.x == 0) {
+        (cm ? a.Q : a.Qp)[at] = r;
         atomicExch(&a.mark[r], 0u);
-        s.S.lvl_begin = 0;
-        s.S.lvl_end = 1;
-        s.S.prev_begin = 0;
-        s.S.depth = 0;
-        s.S.phase = PH_PBFS_LEVEL;
-        s.S.stat_bfs++;
-        s.in_smem = 0;
       }
-      __syncthreads();
+      cur_maxdeg = (unsigned)((int64_t)a.xadj[r + 1] - (int64_t)a.xadj[r]);
+      if (threadIdx.x == 0) {
+        if (cm)
+          s.S.qst = s.S.qwp;
+        else
+          s.S.rlevel = s.S.qlevel;
+        s.S.lvl_begin = at;
+        s.S.lvl_end = at + 1;
+        s.S.prev_begin = at;
+        s.S.depth = 0;
+        s.S.phase = cm ? PH_CM_LEVEL : PH_PBFS_LEVEL;
+        s.S.stat_bfs++;
+      }
+      cluster.sync();  // the root is in the queue for every CTA
       continue;
     }
 
@@ -421,22 +504,24 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
         __syncthreads();
         continue;
       }
-      int c = -1;
-      if (f <= kF && !a.force_wide)
-        c = phase == PH_PBFS_LEVEL ? nw_level<I, N, false>(a, s, a.Qp)
-                                   : nw_level<I, N, true>(a, s, a.Q);
+      long long c = -1;
+      unsigned next_maxdeg = 0;
+      if (!a.force_wide)
+        c = phase == PH_PBFS_LEVEL
+                ? cl_level<I, N, false>(cluster, a, s, a.Qp, par, cur_maxdeg, &next_maxdeg)
+                : cl_level<I, N, true>(cluster, a, s, a.Q, par, cur_maxdeg, &next_maxdeg);
       if (c < 0) {
         __syncthreads();
         if (threadIdx.x == 0) s.S.status = ST_NEED_WIDE;
         break;
       }
+      cur_maxdeg = next_maxdeg;
       if (threadIdx.x == 0) {
         s.S.prev_begin = s.S.lvl_begin;
         s.S.lvl_begin = s.S.lvl_end;
         s.S.lvl_end += c;
         s.S.depth++;
         s.S.stat_levels_narrow++;
-        s.in_smem = 1;
       }
       __syncthreads();
       continue;
@@ -449,12 +534,13 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
       const int64_t visited = s.S.lvl_end;
       const int64_t ecc = s.S.depth - 1;
       const int64_t qlevel = ecc > s.S.qlevel ? ecc : s.S.qlevel;
-      int next;                      // phase after the mark reset
+      int next;  // phase after the mark reset
       int64_t new_root = s.S.root;
       if (visited == qlevel + 1) {
-        next = PH_CM_INIT;           // :58  path-like component: r is the root
+        next = PH_CM_INIT;  // :58  path-like component: r is the root
       } else if (s.S.rlevel != qlevel) {
         // :62-78  eccentricity grew: min degree among the last level, first in queue order
+        // (every CTA scans the whole level: it is short and this keeps the state replicated)
         unsigned long long best = ~0ull;
         for (int64_t k = s.S.prev_begin + threadIdx.x; k < s.S.lvl_begin; k += kNwBlock) {
           const I v = a.Qp[k];
@@ -470,28 +556,25 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
         new_root = (int64_t)a.Qp[s.S.prev_begin + (int64_t)(best & 0xffffffffull)];
         next = PH_PBFS_INIT;
       } else {
-        next = PH_CM_INIT;           // :34  eccentricity did not grow: keep r
+        next = PH_CM_INIT;  // :34  eccentricity did not grow: keep r
       }
       __syncthreads();
       if (threadIdx.x == 0) {
         s.S.qlevel = qlevel;
         s.S.new_root_pending = new_root;
         s.S.next_phase_after_reset = next;
+        s.S.phase = PH_PBFS_AFTER_RESET;
       }
       __syncthreads();
       // un-visit everything this BFS touched (mark[] doubles as distance[] and V[])
       if (visited > kBulkThreshold) {
-        if (threadIdx.x == 0) {
-          s.S.phase = PH_PBFS_AFTER_RESET;
-          s.S.status = ST_NEED_RESET;
-        }
+        if (threadIdx.x == 0) s.S.status = ST_NEED_RESET;
         break;
       }
-      for (int64_t k = threadIdx.x; k < visited; k += kNwBlock)
+      for (int64_t k = (int64_t)rank * kNwBlock + threadIdx.x; k < visited;
+           k += (int64_t)C * kNwBlock)
         atomicExch(&a.mark[a.Qp[k]], kUnvisited);
-      __syncthreads();
-      if (threadIdx.x == 0) s.S.phase = PH_PBFS_AFTER_RESET;
-      __syncthreads();
+      cluster.sync();
       continue;
     }
 
@@ -504,54 +587,33 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
       continue;
     }
 
-    // ================================================================ Cuthill-McKee BFS
-    if (phase == PH_CM_INIT) {  // rcm_reorder.cc:119-123
-      if (threadIdx.x == 0) {
-        const I r = (I)s.S.root;
-        s.S.qst = s.S.qwp;
-        a.Q[s.S.qwp] = r;
-        atomicExch(&a.mark[r], 0u);
-        s.S.lvl_begin = s.S.qwp;
-        s.S.lvl_end = s.S.qwp + 1;
-        s.S.prev_begin = s.S.qwp;
-        s.S.depth = 0;
-        s.S.phase = PH_CM_LEVEL;
-        s.S.stat_bfs++;
-        s.in_smem = 0;
-      }
-      __syncthreads();
-      continue;
-    }
-
+    // ================================================================ Cuthill-McKee end
     if (phase == PH_CM_END) {
       // component = Q[qst, lvl_end); reversed slice + final inversion (:147-160):
       // inv[Q[k]] = qst + (end-1-k)
       const int64_t qst = s.S.qst, end = s.S.lvl_end;
-      if (threadIdx.x == 0) s.S.qwp = end;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        s.S.qwp = end;
+        s.S.phase = PH_FIND;
+      }
+      __syncthreads();
       if (end - qst > kBulkThreshold) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          s.S.phase = PH_CM_AFTER_INVERT;
-          s.S.status = ST_NEED_INVERT;
-        }
+        if (threadIdx.x == 0) s.S.status = ST_NEED_INVERT;
         break;
       }
-      for (int64_t k = qst + threadIdx.x; k < end; k += kNwBlock)
+      for (int64_t k = qst + (int64_t)rank * kNwBlock + threadIdx.x; k < end;
+           k += (int64_t)C * kNwBlock)
         a.inv[a.Q[k]] = (I)(qst + (end - 1 - k));
-      __syncthreads();
-      if (threadIdx.x == 0) s.S.phase = PH_CM_AFTER_INVERT;
-      __syncthreads();
-      continue;
-    }
-
-    if (phase == PH_CM_AFTER_INVERT) {
-      if (threadIdx.x == 0) s.S.phase = PH_FIND;
-      __syncthreads();
+      cluster.sync();
       continue;
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) *a.state = s.S;
+  if (rank == 0 && threadIdx.x == 0) {
+    s.S.frontier_maxdeg = cur_maxdeg;
+    *a.state = s.S;
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -605,6 +667,7 @@ __global__ void __launch_bounds__(256)
                             const I *__restrict__ adj, const unsigned *__restrict__ mark,
                             uint64_t *__restrict__ ckey, uint32_t *__restrict__ cval,
                             unsigned long long *__restrict__ counter) {
+  // counter[0] = number of winners, counter[1] = max degree among them
   const unsigned lane = lane_id();
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -634,13 +697,10 @@ __global__ void __launch_bounds__(256)
         base = __shfl_sync(0xffffffffu, base, 0);
         if (win) {
           const unsigned long long k = base + __popc(bal & lanemask_lt());
-          uint64_t ok;
-          if (CM)
-            ok = ((uint64_t)(key - 1u) << 32) | (uint64_t)(unsigned)(xadj[v + 1] - xadj[v]);
-          else
-            ok = (uint64_t)(key - 1u);
-          ckey[k] = ok;
+          const unsigned dg = (unsigned)(xadj[v + 1] - xadj[v]);
+          ckey[k] = CM ? (((uint64_t)(key - 1u) << 32) | (uint64_t)dg) : (uint64_t)(key - 1u);
           cval[k] = (uint32_t)v;
+          atomicMax(counter + 1, (unsigned long long)dg);
         }
       }
     });
@@ -703,7 +763,7 @@ void rcm_wide_level(Workspace &ws, const RcmArgs<I, N> &a, WideCtx<I, N> &w, Rcm
   const int64_t f = S.lvl_end - S.lvl_begin;
   const int grid = device_info(ws.device()).sm_count * 8;
   exclusive_scan<int64_t>(ws, FrontierDegFn<I, N>{frontier, a.xadj}, w.off, f);
-  SB_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(unsigned long long), st));
+  SB_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(unsigned long long), st));
   if (cm) {
     SB_LAUNCH((rcm_wide_claim_kernel<I, N, true>), grid, 256, 0, st, frontier, f,
               (const int64_t *)w.off, a.xadj, a.adj, a.mark);
@@ -717,11 +777,13 @@ void rcm_wide_level(Workspace &ws, const RcmArgs<I, N> &a, WideCtx<I, N> &w, Rcm
               (const int64_t *)w.off, a.xadj, a.adj, (const unsigned *)a.mark, w.k0, w.v0,
               w.counter);
   }
-  unsigned long long c = 0;
+  unsigned long long cnt2[2] = {0, 0};
   int64_t slots = 0;
-  SB_CUDA(cudaMemcpyAsync(&c, w.counter, sizeof(c), cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(cnt2, w.counter, sizeof(cnt2), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(&slots, w.off + f, sizeof(slots), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
+  const unsigned long long c = cnt2[0];
+  S.frontier_maxdeg = (int64_t)cnt2[1];
   SB_REQUIRE(slots < 0xfffffffell, SB200_ERR_BAD_ARG,
              "RCM level with %lld expansion slots exceeds the 32-bit claim key", (long long)slots);
   if (c > 0) {
@@ -785,7 +847,7 @@ void rcm_impl(Workspace &ws, int64_t n, int64_t nnz, const N *xadj, const I *adj
     w.v0 = ws.alloc<uint32_t>(n);
     w.v1 = ws.alloc<uint32_t>(n);
     w.v2 = ws.alloc<uint32_t>(n);
-    w.counter = ws.alloc<unsigned long long>(1);
+    w.counter = ws.alloc<unsigned long long>(2);
     unsigned long long *md = ws.alloc<unsigned long long>(1);
     SB_CUDA(cudaMemsetAsync(md, 0, sizeof(*md), st));
     SB_LAUNCH((max_degree_kernel<N>), device_info(ws.device()).sm_count * 8, 256, 0, st, xadj, n,
@@ -801,9 +863,32 @@ void rcm_impl(Workspace &ws, int64_t n, int64_t nnz, const N *xadj, const I *adj
 
   auto kern = rcm_narrow_kernel<I, N>;
   SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)sizeof(NwSmem<I>)));
+                               (int)sizeof(ClSmem<I>)));
+  SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  cfg.blockDim = dim3(kNwBlock, 1, 1);
+  cfg.dynamicSmemBytes = sizeof(ClSmem<I>);
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int cluster = kClMax;
+  for (; cluster >= 1; cluster >>= 1) {  // largest cluster the device can co-schedule
+    cfg.gridDim = dim3(cluster, 1, 1);
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    int nclusters = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
+    if (e == cudaSuccess && nclusters >= 1) break;
+    cudaGetLastError();
+  }
+  SB_REQUIRE(cluster >= 1, SB200_ERR_CUDA, "cannot launch the RCM cluster kernel");
+  const int64_t narrow_cap = (int64_t)cluster * kFl;
   for (;;) {
-    SB_LAUNCH(kern, 1, kNwBlock, sizeof(NwSmem<I>), st, a);
+    SB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    launch_counter()++;
     SB_CUDA(cudaMemcpyAsync(&S, a.state, sizeof(S), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
     if (S.status == ST_DONE) break;
@@ -813,7 +898,7 @@ void rcm_impl(Workspace &ws, int64_t n, int64_t nnz, const N *xadj, const I *adj
       // keep going wide while the frontier is far beyond the narrow capacity
       do {
         rcm_wide_level<I, N>(ws, a, w, S, cm);
-      } while (S.lvl_end - S.lvl_begin > (force_wide ? 0 : 4 * NwCaps<I>::kF));
+      } while (S.lvl_end - S.lvl_begin > (force_wide ? 0 : narrow_cap));
     } else if (S.status == ST_NEED_RESET) {
       const int64_t cnt = S.lvl_end;
       SB_LAUNCH((rcm_reset_kernel<I>), (unsigned)ceil_div(cnt, 256), 256, 0, st, (const I *)a.Qp,

@@ -23,8 +23,8 @@
 namespace sb200 {
 
 constexpr int kSsBlock = 256;
-constexpr int kSsTile = 2048;  // window of output positions per CTA
-constexpr int kSsLong = 2048;  // longest segment sorted on chip (must be >= kSsTile)
+constexpr int kSsTile = 1024;  // window of output positions per CTA
+constexpr int kSsLong = 1024;  // longest segment sorted on chip (must be >= kSsTile)
 constexpr int kSsCap = kSsTile + kSsLong;
 constexpr int kSsEnum = 32;
 constexpr int kSsMaxMid = kSsCap / (kSsEnum + 1) + 1;
@@ -55,12 +55,12 @@ template <typename I, typename V>
 struct SsSmem {
   I key[kSsCap];
   typename std::conditional<has_val<V>, V, char>::type val[has_val<V> ? kSsCap : 1];
-  int64_t src_base[kSsTile];
-  unsigned short lrow[kSsCap];
-  unsigned short rstart[kSsTile + 1];
-  unsigned short mid[kSsMaxMid];
+  unsigned lrow[kSsCap];          // segment number (relative to the window's first) per entry
+  unsigned short sbeg[kSsCap];    // local start / end of the entry's segment
+  unsigned short send[kSsCap];
+  unsigned mid[kSsMaxMid];        // segments of 33..kSsLong entries (relative numbers)
   unsigned scratch[34];
-  unsigned nlr, nmid;
+  unsigned nmid;
 };
 
 template <typename I, typename V>
@@ -99,43 +99,23 @@ __global__ void __launch_bounds__(kSsBlock)
   const int count = (int)((int64_t)ptr[r1] - first);
   if (count == 0) return;
 
-  if (threadIdx.x == 0) {
-    s.nlr = 0;
-    s.nmid = 0;
-  }
+  if (threadIdx.x == 0) s.nmid = 0;
   for (int q = threadIdx.x; q < count; q += kSsBlock) s.lrow[q] = 0;
   __syncthreads();
 
-  // ---- pass over the window's segments: number the non-empty ones, record their local
-  //      start, their source base and the list of "mid" (33..kSsLong) segments ----
-  for (int64_t rb = r0; rb < r1; rb += kSsBlock) {
-    const int64_t r = rb + threadIdx.x;
-    int64_t sbeg = 0, send = 0;
-    if (r < r1) {
-      sbeg = (int64_t)ptr[r] - first;
-      send = (int64_t)ptr[r + 1] - first;
+  // ---- every non-empty segment marks its first position with (relative number + 1) ----
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += kSsBlock) {
+    const int64_t sb = (int64_t)ptr[r] - first, se = (int64_t)ptr[r + 1] - first;
+    if (se > sb) {
+      s.lrow[sb] = (unsigned)(r - r0) + 1u;
+      if (se - sb > kSsEnum) s.mid[atomicAdd(&s.nmid, 1u)] = (unsigned)(r - r0);
     }
-    const unsigned nonempty = send > sbeg ? 1u : 0u;
-    unsigned total;
-    unsigned lr = block_exclusive_scan(nonempty, s.scratch, &total);
-    const unsigned base = s.nlr;
-    if (nonempty) {
-      lr += base;
-      s.rstart[lr] = (unsigned short)sbeg;
-      s.lrow[sbeg] = (unsigned short)(lr + 1);
-      s.src_base[lr] = ld.seg_base(r);
-      if (send - sbeg > kSsEnum) s.mid[atomicAdd(&s.nmid, 1u)] = (unsigned short)lr;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s.nlr = base + total;
-    __syncthreads();
   }
-  const unsigned nlr = s.nlr;
-  if (threadIdx.x == 0) s.rstart[nlr] = (unsigned short)count;
+  __syncthreads();
 
-  // ---- propagate segment numbers to every position: inclusive max-scan of the head marks ----
+  // ---- propagate segment numbers to every position: inclusive max-scan of the marks ----
   {
-    constexpr int kPer = kSsCap / kSsBlock;  // 16 consecutive positions per thread
+    constexpr int kPer = kSsCap / kSsBlock;  // consecutive positions per thread
     const int q0 = threadIdx.x * kPer;
     unsigned m = 0;
 #pragma unroll
@@ -144,14 +124,12 @@ __global__ void __launch_bounds__(kSsBlock)
       unsigned h = q < count ? s.lrow[q] : 0u;
       m = h > m ? h : m;
     }
-    // exclusive max-scan across threads
     unsigned inc = m;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       unsigned tt = __shfl_up_sync(0xffffffffu, inc, o);
       if ((int)lane >= o) inc = tt > inc ? tt : inc;
     }
-    __syncthreads();
     if (lane == 31) s.scratch[wid] = inc;
     __syncthreads();
     unsigned carry = 0;
@@ -165,7 +143,7 @@ __global__ void __launch_bounds__(kSsBlock)
       if (q < count) {
         unsigned h = s.lrow[q];
         run = h > run ? h : run;
-        s.lrow[q] = (unsigned short)(run - 1);
+        s.lrow[q] = run - 1u;
       }
     }
   }
@@ -176,12 +154,15 @@ __global__ void __launch_bounds__(kSsBlock)
   for (int qb = 0; qb < count; qb += kSsBlock * 8) {
     I k[8];
     [[maybe_unused]] typename std::conditional<has_val<V>, V, char>::type v[8];
+    int sb[8], se[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) {
       const int q = qb + u * kSsBlock + (int)threadIdx.x;
       if (q < count) {
-        const unsigned lr = s.lrow[q];
-        const int64_t p = s.src_base[lr] + (q - (int)s.rstart[lr]);
+        const int64_t r = r0 + s.lrow[q];
+        sb[u] = (int)((int64_t)ptr[r] - first);
+        se[u] = (int)((int64_t)ptr[r + 1] - first);
+        const int64_t p = ld.seg_base(r) + (q - sb[u]);
         k[u] = ld.key(p);
         if constexpr (has_val<V>) v[u] = ld.val(p);
       }
@@ -192,6 +173,8 @@ __global__ void __launch_bounds__(kSsBlock)
       if (q < count) {
         s.key[q] = k[u];
         if constexpr (has_val<V>) s.val[q] = v[u];
+        s.sbeg[q] = (unsigned short)sb[u];
+        s.send[q] = (unsigned short)se[u];
       }
     }
   }
@@ -199,8 +182,7 @@ __global__ void __launch_bounds__(kSsBlock)
 
   // ---- short segments: rank by enumeration, write straight to the final position ----
   for (int q = threadIdx.x; q < count; q += kSsBlock) {
-    const unsigned lr = s.lrow[q];
-    const int sb = s.rstart[lr], se = s.rstart[lr + 1];
+    const int sb = s.sbeg[q], se = s.send[q];
     if (se - sb > kSsEnum) continue;
     const I k = s.key[q];
     int rank = 0;
@@ -215,8 +197,8 @@ __global__ void __launch_bounds__(kSsBlock)
   // ---- mid segments: one warp each, normalized bitonic network in shared memory ----
   const unsigned nmid = s.nmid;
   for (unsigned mi = wid; mi < nmid; mi += kSsBlock / 32) {
-    const unsigned lr = s.mid[mi];
-    const int sb = s.rstart[lr], len = (int)s.rstart[lr + 1] - sb;
+    const int64_t r = r0 + s.mid[mi];
+    const int sb = (int)((int64_t)ptr[r] - first), len = (int)((int64_t)ptr[r + 1] - ptr[r]);
     I *key = s.key + sb;
     int P = 64;
     while (P < len) P <<= 1;
