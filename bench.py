@@ -271,7 +271,8 @@ def main():
     # ---- other operators of the path on the same matrix (reported, not the headline) ----
     peak, peak_src = peaks()
     ops = {"rcm_reorder": {"ms": rcm_ms, "levels_narrow": rcm_stats["levels_narrow"],
-                           "levels_wide": rcm_stats["levels_wide"], "bfs": rcm_stats["bfs"]}}
+                           "levels_wide": rcm_stats["levels_wide"], "bfs": rcm_stats["bfs"],
+                           "phase_cycles": rcm_stats["phase_cycles"]}}
 
     def time_op(name, fn, reps=5):
         fn()

@@ -26,8 +26,8 @@ namespace sb200 {
 
 constexpr int kRsBlock = 256;
 constexpr int kRsWarps = kRsBlock / 32;
-constexpr int kRsIpt = 16;
-constexpr int kRsTile = kRsBlock * kRsIpt;  // 4096 records per tile
+constexpr int kRsIpt = 12;
+constexpr int kRsTile = kRsBlock * kRsIpt;  // 3072 records per tile
 constexpr int kRsMaxBits = 8;
 constexpr int kRsMaxBins = 1 << kRsMaxBits;
 
@@ -162,6 +162,18 @@ __global__ void __launch_bounds__(kRsBlock, 2)
   if ((int)threadIdx.x < nbins)
     s.bin_off[threadIdx.x] = spine[(int64_t)threadIdx.x * ch.nchunks + c];
 
+  // software pipeline: the keys of tile t+1 are requested before tile t is processed, so the
+  // ranking of a tile never waits for its own loads (ncu: 37% of the stall samples sat on the
+  // first use of the freshly loaded keys before this)
+  K key[kRsIpt], nkey[kRsIpt];
+  {
+    const int64_t wb = ch.tile_begin(c) * kRsTile + (int64_t)wid * (kRsIpt * 32);
+#pragma unroll
+    for (int r = 0; r < kRsIpt; r++) {
+      int64_t i = wb + r * 32 + lane;
+      nkey[r] = i < n ? ld_stream(kin + i) : K(0);
+    }
+  }
   for (int64_t tile = ch.tile_begin(c); tile < ch.tile_end(c); tile++) {
     const int64_t tile_base_idx = tile * kRsTile;
     const int64_t rem = n - tile_base_idx;
@@ -170,14 +182,16 @@ __global__ void __launch_bounds__(kRsBlock, 2)
 
     for (int i = threadIdx.x; i < kRsWarps * kRsMaxBins; i += kRsBlock) (&s.cnt[0][0])[i] = 0;
 
-    // all global loads of the tile are issued up front (keys and both payloads): one memory
-    // round trip per tile, 16 x (sizeof key + payloads) bytes in flight per thread
-    K key[kRsIpt];
 #pragma unroll
-    for (int r = 0; r < kRsIpt; r++) {
-      int64_t i = warp_base + r * 32 + lane;
-      key[r] = i < n ? ld_stream(kin + i) : K(0);
+    for (int r = 0; r < kRsIpt; r++) key[r] = nkey[r];
+    if (tile + 1 < ch.tile_end(c)) {
+#pragma unroll
+      for (int r = 0; r < kRsIpt; r++) {
+        int64_t i = warp_base + kRsTile + r * 32 + lane;
+        nkey[r] = i < n ? ld_stream(kin + i) : K(0);
+      }
     }
+    // payload loads of this tile are issued now and consumed after the ranking
     [[maybe_unused]] typename std::conditional<has_val<V1>, V1, char>::type p1[kRsIpt];
     [[maybe_unused]] typename std::conditional<has_val<V2>, V2, char>::type p2[kRsIpt];
     if constexpr (has_val<V1>) rs_load_payload<V1>(v1in, warp_base, n, p1);

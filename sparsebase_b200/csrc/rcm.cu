@@ -62,6 +62,7 @@ struct RcmState {
   int64_t frontier_maxdeg;  // max degree over the current frontier (for the narrow caps)
   int64_t inv_qst, inv_end;  // pending bulk inversion
   int64_t stat_levels_narrow, stat_levels_wide, stat_bfs, stat_components;
+  int64_t cyc[8];  // narrow-level phase cycle counters (CTA 0): load, claim, check, finalize, write
 };
 
 __device__ __forceinline__ int bits_for_dev(unsigned long long v) {
@@ -217,6 +218,13 @@ __device__ long long cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a
   const int jbits = bits_for_dev(cur_maxdeg);
   if (!CM && bits_for_dev((unsigned long long)f) + jbits > 31) return -1;
   const bool need_check = (unsigned long long)max_share * cur_maxdeg > (unsigned long long)kEl;
+  long long t0 = clock64(), t1;
+#define SB_TICK(slot)                                   \
+  do {                                                  \
+    t1 = clock64();                                     \
+    if (threadIdx.x == 0) s.S.cyc[slot] += t1 - t0;     \
+    t0 = t1;                                            \
+  } while (0)
 
   // ---- my share of the frontier: vertex, adjacency start, degree ----
   for (int i = threadIdx.x; i < fl; i += kNwBlock) {
@@ -253,6 +261,7 @@ __device__ long long cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a
   start.rem = 0;
   start.p = 0;
   if (s0 < total) start.seek(s, fl, s0);
+  SB_TICK(0);
 
   // ---- sweep 1: claims.  key orders (global frontier position[, adjacency index]) ----
   I v[kClSpt];
@@ -274,10 +283,17 @@ __device__ long long cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a
     for (int u = 0; u < kClSpt; u++)
       if (s0 + u < s1) old[u] = atomicMin(&a.mark[v[u]], key[u]);
 #pragma unroll
-    for (int u = 0; u < kClSpt; u++)
-      if (s0 + u < s1 && old[u] > key[u]) prov |= 1u << u;
+    for (int u = 0; u < kClSpt; u++) {
+      if (s0 + u < s1 && old[u] > key[u]) {
+        prov |= 1u << u;
+        // a provisional winner's adjacency extent is read in the finalize phase: start the
+        // DRAM access now so that it overlaps the barrier and the check phase
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.xadj + v[u]));
+      }
+    }
   }
   cluster.sync();
+  SB_TICK(1);
 
   // ---- sweep 2: which provisional winners survived? ----
   unsigned wbits = 0, wcount = 0;
@@ -312,6 +328,7 @@ __device__ long long cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a
     }
   }
   __syncthreads();
+  SB_TICK(2);
 
   // ---- new vertices: mark visited, fetch their adjacency extent ----
   const int c = (int)c_local;
@@ -347,6 +364,7 @@ __device__ long long cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a
     nmax = mk > nmax ? mk : nmax;
   }
   *next_maxdeg = nmax;
+  SB_TICK(3);
 
   // ---- next frontier: slot order (peripheral) or (parent, degree, id) order (CM); the
   //      sibling groups of a parent never leave the CTA that owns the parent ----
@@ -370,6 +388,8 @@ __device__ long long cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a
     asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + s.cx[k]));
   }
   cluster.sync();  // the queue slice is complete and visible to every CTA
+  SB_TICK(4);
+#undef SB_TICK
   return ctotal;
 }
 
@@ -951,6 +971,14 @@ int sb200_rcm_last_stats(int64_t *h_out4) {
   h_out4[1] = g_last_rcm_stats.stat_levels_wide;
   h_out4[2] = g_last_rcm_stats.stat_bfs;
   h_out4[3] = g_last_rcm_stats.stat_components;
+  return SB200_OK;
+}
+
+// Cycle counters of the cluster kernel's level phases (CTA 0): load, claim, check, finalize,
+// write -- a profiling aid, not part of the reference-facing surface.
+int sb200_rcm_last_cycles(int64_t *h_out8) {
+  if (!h_out8) return SB200_ERR_BAD_ARG;
+  for (int i = 0; i < 8; i++) h_out8[i] = g_last_rcm_stats.cyc[i];
   return SB200_OK;
 }
 

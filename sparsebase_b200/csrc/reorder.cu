@@ -124,27 +124,29 @@ void degree_reorder_impl(Workspace &ws, int64_t n, const N *row_ptr, bool ascend
 }
 
 // ---------------------------------------------------------------- Permute2D
+// Old row i becomes new row j = row_order[i].  One coalesced pass over xadj scatters, per new
+// row, the source offset of its first entry and its length; the scan and the tile kernel then
+// read both arrays coalesced (no dependent irow -> xadj gathers inside the hot kernel).
 template <typename I, typename N>
-struct PermutedLenFn {  // length of new row i = length of old row irow[i]
-  const N *xadj;
-  const I *irow;  // may be null (identity)
-  __device__ N operator()(int64_t i) const {
-    const int64_t u = irow ? (int64_t)irow[i] : i;
-    return xadj[u + 1] - xadj[u];
+__global__ void permute_prepare_kernel(const N *__restrict__ xadj, const I *__restrict__ row_order,
+                                       int64_t n, int64_t *__restrict__ src_base,
+                                       N *__restrict__ new_len) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int64_t j = row_order ? (int64_t)row_order[i] : i;
+    const N b = xadj[i], e = xadj[i + 1];
+    src_base[j] = (int64_t)b;
+    new_len[j] = e - b;
   }
-};
+}
 
 template <typename I, typename N, typename V>
 struct GatherLoader {
-  const N *xadj;
+  const int64_t *src_base;  // per new row: offset of the old row's first entry
   const I *adj;
   const V *vals;
-  const I *irow;       // new row -> old row, or null
   const I *col_order;  // old col -> new col, or null
-  __device__ int64_t seg_base(int64_t r) const {
-    const int64_t u = irow ? (int64_t)irow[r] : r;
-    return (int64_t)xadj[u];
-  }
+  __device__ int64_t seg_base(int64_t r) const { return src_base[r]; }
   __device__ I key(int64_t p) const {
     const I c = ld_stream(adj + p);
     return col_order ? col_order[c] : c;
@@ -157,13 +159,13 @@ void permute2d_impl(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const N *x
                     const I *adj, const V *vals, const I *row_order, const I *col_order,
                     N *out_row_ptr, I *out_col, V *out_vals) {
   cudaStream_t st = ws.stream();
-  I *irow = nullptr;
-  if (row_order && n > 0) {
-    irow = ws.alloc<I>(n);
-    SB_LAUNCH((inverse_permutation_kernel<I>), map_grid(n), kMapBlock, 0, st, row_order, n, irow);
-  }
-  exclusive_scan<N>(ws, PermutedLenFn<I, N>{xadj, irow}, out_row_ptr, n);
-  GatherLoader<I, N, V> ld{xadj, adj, vals, irow, col_order};
+  int64_t *src_base = ws.alloc<int64_t>(n + 1);
+  N *new_len = ws.alloc<N>(n + 1);
+  if (n > 0)
+    SB_LAUNCH((permute_prepare_kernel<I, N>), map_grid(n), kMapBlock, 0, st, xadj, row_order, n,
+              src_base, new_len);
+  exclusive_scan<N>(ws, LoadFn<N>{new_len}, out_row_ptr, n);
+  GatherLoader<I, N, V> ld{src_base, adj, vals, col_order};
   segmented_sort<I, N, V>(ws, ld, (const N *)out_row_ptr, n, m, nnz, out_col, out_vals);
 }
 

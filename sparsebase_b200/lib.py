@@ -23,7 +23,7 @@ SYMBOLS = [
     "sb200_free_host", "sb200_memcpy_h2d", "sb200_memcpy_d2h", "sb200_memcpy_d2d",
     "sb200_stream_synchronize", "sb200_coo_sort", "sb200_compressed_sort", "sb200_coo_to_csr",
     "sb200_csr_to_coo", "sb200_coo_to_csc", "sb200_csr_to_csc", "sb200_degree_reorder",
-    "sb200_rcm_reorder", "sb200_rcm_last_stats", "sb200_permute2d", "sb200_permute1d", "sb200_inverse_permutation",
+    "sb200_rcm_reorder", "sb200_rcm_last_stats", "sb200_rcm_last_cycles", "sb200_permute2d", "sb200_permute1d", "sb200_inverse_permutation",
     "sb200_degrees", "sb200_degree_distribution", "sb200_partition_rows", "sb200_launch_count",
     "sb200_reset_launch_count",
 ]
@@ -183,7 +183,11 @@ def rcm_reorder(n, row_ptr, col):
 def rcm_last_stats():
     out = (ctypes.c_int64 * 4)()
     _check(load().sb200_rcm_last_stats(out))
-    return dict(zip(("levels_narrow", "levels_wide", "bfs", "components"), list(out)))
+    d = dict(zip(("levels_narrow", "levels_wide", "bfs", "components"), list(out)))
+    cyc = (ctypes.c_int64 * 8)()
+    _check(load().sb200_rcm_last_cycles(cyc))
+    d["phase_cycles"] = dict(zip(("load", "claim", "check", "finalize", "write"), list(cyc)[:5]))
+    return d
 
 
 # ------------------------------------------------------------------ permutation
