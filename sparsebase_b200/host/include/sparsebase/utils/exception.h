@@ -1,0 +1,3 @@
+// Same include path as the reference's src/sparsebase/utils/exception.h; the B200 host layer lives in sb200/.
+#pragma once
+#include "../../sb200/core.h"
