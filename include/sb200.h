@@ -22,7 +22,10 @@
  *                             converter/converter_order_one_cuda.cu:10-43, utils/utils_cuda.cuh:6-9
  *   sb200_can_access_peer     converter/converter_cuda.cu:12-21 (CUDAPeerToPeer)
  *   sb200_device_count        context/cuda_context_cuda.cu:9-15 (CUDAContext ctor validation)
- *   sb200_partition_rows      (new) nnz-balanced contiguous row blocks for the multi-GPU path
+ *   sb200_partition_rows, sb200_*_block, sb200_exclusive_scan, sb200_rank_keys,
+ *   sb200_max_degree, sb200_degree_histogram, sb200_degree_rank_combine
+ *                             (new) per-GPU pieces of the row-block sharded multi-GPU path; the
+ *                             reference has no distributed code
  *
  * Conventions
  *  - Plain C: pointers and sizes only, no C++/torch types.  Every function returns 0 on
@@ -180,6 +183,41 @@ int sb200_degree_distribution(int device, int64_t n, int64_t nnz, const void *ro
  * row_ptr >= k*nnz/parts.  Synchronises the stream. */
 int sb200_partition_rows(int device, int64_t n, int64_t nnz, const void *row_ptr, int nnz_type,
                          int parts, int64_t *h_bounds, void *stream);
+
+/* Row-block variants: the caller owns rows [row_lo, row_lo + n_local) of an n x m matrix.
+ * coo_to_csr_block: row[] holds GLOBAL row ids of that block; out_row_ptr[n_local+1] holds
+ * block-local offsets.  csr_to_csc_block: row_ptr[n_local+1] is block-local; out_col_ptr has
+ * m+1 entries (one per global column) and out_row holds GLOBAL row ids. */
+int sb200_coo_to_csr_block(int device, int64_t row_lo, int64_t n_local, int64_t m, int64_t nnz,
+                           const void *row, const void *col, const void *vals,
+                           void *out_row_ptr, void *out_col, void *out_vals, int id_type,
+                           int nnz_type, int val_type, void *stream);
+int sb200_csr_to_csc_block(int device, int64_t row_lo, int64_t n_local, int64_t m, int64_t nnz,
+                           const void *row_ptr, const void *col, const void *vals,
+                           void *out_col_ptr, void *out_row, void *out_vals, int id_type,
+                           int nnz_type, int val_type, void *stream);
+
+/* out[0..n] (n+1 entries) = exclusive prefix sums of in[0..n-1]; dtype in {I32,U32,I64,U64}. */
+int sb200_exclusive_scan(int device, int64_t n, const void *in, void *out, int dtype,
+                         void *stream);
+
+/* out_rank[i] = number of keys smaller than keys[i]; keys must be distinct and < key_bound. */
+int sb200_rank_keys(int device, int64_t n, const void *keys, int64_t key_bound, void *out_rank,
+                    int id_type, void *stream);
+
+/* *h_out = max_i (row_ptr[i+1] - row_ptr[i]).  Synchronises the stream. */
+int sb200_max_degree(int device, int64_t n, const void *row_ptr, int nnz_type, int64_t *h_out,
+                     void *stream);
+
+/* out_hist[d] (uint64, nbins entries, zeroed here) = number of rows with degree d. */
+int sb200_degree_histogram(int device, int64_t n, const void *row_ptr, int nnz_type,
+                           int64_t nbins, void *out_hist, void *stream);
+
+/* out[i] = local_rank[i] + offset[degree(i)] (offset: int64 table indexed by degree); with
+ * flip_from >= 0 the result is flip_from - that (DegreeReorder descending = reversed order). */
+int sb200_degree_rank_combine(int device, int64_t n, const void *row_ptr, const void *local_rank,
+                              const void *offset, int64_t flip_from, void *out, int id_type,
+                              int nnz_type, void *stream);
 
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */

@@ -32,7 +32,7 @@ template <typename I, typename N, typename V>
 __global__ void __launch_bounds__(kBfBlock)
     boundary_fill_copy_kernel(const I *__restrict__ idx, const I *__restrict__ sec,
                               const V *__restrict__ vals, int64_t nnz, int64_t n_seg,
-                              N *__restrict__ ptr, I *__restrict__ out_sec,
+                              I idx_base, N *__restrict__ ptr, I *__restrict__ out_sec,
                               V *__restrict__ out_vals, unsigned *__restrict__ flags) {
   const int64_t base = ((int64_t)blockIdx.x * kBfBlock) * kBfIpt;
   bool inv = false, sec_unsorted = false;
@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(kBfBlock)
   for (int k = 0; k < kBfIpt; k++) {
     const int64_t i = base + (int64_t)k * kBfBlock + threadIdx.x;
     if (i < nnz) {
-      my[k] = ld_stream(idx + i);
-      prev[k] = i > 0 ? idx[i - 1] : I(0);
+      my[k] = ld_stream(idx + i) - idx_base;
+      prev[k] = i > 0 ? idx[i - 1] - idx_base : I(0);
       if (sec) {
         ms[k] = ld_stream(sec + i);
         ps[k] = i > 0 ? sec[i - 1] : I(0);
@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(kBfBlock)
       int64_t lo = i > 0 ? (int64_t)prev[k] + 1 : 0;
       int64_t hi = (int64_t)my[k];
       if (hi >= n_seg) hi = n_seg - 1;  // indices >= n_seg are not representable (see header)
+      if (lo < 0) lo = 0;
       for (int64_t r = lo; r <= hi; r++) ptr[r] = (N)i;
       if (i == nnz - 1)
         for (int64_t r = (int64_t)my[k] + 1; r <= n_seg; r++) ptr[r] = (N)nnz;
@@ -87,10 +88,10 @@ __global__ void fill_kernel(N *p, int64_t cnt, N v) {
 //      row histogram with warp-aggregated atomics, then the scan ----
 template <typename I>
 __global__ void histogram_kernel(const I *__restrict__ idx, int64_t nnz, int64_t n_seg,
-                                 unsigned long long *__restrict__ hist) {
+                                 I idx_base, unsigned long long *__restrict__ hist) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const I r = idx[i];
+    const I r = idx[i] - idx_base;
     if ((int64_t)r >= n_seg || r < 0) continue;
     // warp-aggregated: one atomic per distinct row among the active lanes
     const unsigned act = __activemask();
@@ -110,7 +111,8 @@ struct HistFn {
 // Returns flags {stream had inversions, some compressed segment is unsorted}.
 template <typename I, typename N, typename V>
 void build_ptr_and_copy(Workspace &ws, const I *idx, const I *sec, const V *vals, int64_t nnz,
-                        int64_t n_seg, N *ptr, I *out_sec, V *out_vals, unsigned h_flags[2]) {
+                        int64_t n_seg, N *ptr, I *out_sec, V *out_vals, unsigned h_flags[2],
+                        I idx_base = 0) {
   cudaStream_t st = ws.stream();
   unsigned *flags = ws.alloc<unsigned>(2);
   SB_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(unsigned), st));
@@ -121,14 +123,14 @@ void build_ptr_and_copy(Workspace &ws, const I *idx, const I *sec, const V *vals
   }
   const int64_t per_block = (int64_t)kBfBlock * kBfIpt;
   SB_LAUNCH((boundary_fill_copy_kernel<I, N, V>), (unsigned)ceil_div(nnz, per_block), kBfBlock,
-            0, st, idx, sec, vals, nnz, n_seg, ptr, out_sec, out_vals, flags);
+            0, st, idx, sec, vals, nnz, n_seg, idx_base, ptr, out_sec, out_vals, flags);
   SB_CUDA(cudaMemcpyAsync(h_flags, flags, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   if (h_flags[0]) {
     unsigned long long *hist = ws.alloc<unsigned long long>(n_seg + 1);
     SB_CUDA(cudaMemsetAsync(hist, 0, (n_seg + 1) * sizeof(unsigned long long), st));
     SB_LAUNCH((histogram_kernel<I>), device_info(ws.device()).sm_count * 8, 256, 0, st, idx, nnz,
-              n_seg, hist);
+              n_seg, idx_base, hist);
     exclusive_scan<N>(ws, HistFn<N>{hist}, ptr, n_seg);
   }
 }
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(kExBlock)
     expand_ptr_kernel(const N *__restrict__ ptr, const int64_t *__restrict__ tile_seg,
                       int64_t nnz, const I *__restrict__ col, const V *__restrict__ vals,
                       I *__restrict__ out_row, I *__restrict__ out_col,
-                      V *__restrict__ out_vals) {
+                      V *__restrict__ out_vals, I row_base) {
   __shared__ long long mark[kExTile];
   __shared__ long long warp_max[kExBlock / 32];
   const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(kExBlock)
   }
   __syncthreads();
   for (int q = threadIdx.x; q < count; q += kExBlock) {
-    st_stream(out_row + w0 + q, (I)mark[q]);
+    st_stream(out_row + w0 + q, (I)mark[q] + row_base);
     if (out_col) st_stream(out_col + w0 + q, ld_stream(col + w0 + q));
     if constexpr (has_val<V>) {
       if (out_vals) st_stream(out_vals + w0 + q, ld_stream(vals + w0 + q));
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(kExBlock)
 
 template <typename I, typename N, typename V>
 void expand_ptr(Workspace &ws, const N *ptr, int64_t n_seg, int64_t nnz, const I *col,
-                const V *vals, I *out_row, I *out_col, V *out_vals) {
+                const V *vals, I *out_row, I *out_col, V *out_vals, I row_base = 0) {
   if (nnz <= 0) return;
   cudaStream_t st = ws.stream();
   const int64_t ntiles = ceil_div(nnz, kExTile);
@@ -363,7 +365,7 @@ void expand_ptr(Workspace &ws, const N *ptr, int64_t n_seg, int64_t nnz, const I
   SB_LAUNCH((ex_tile_bounds_kernel<N>), (unsigned)ceil_div(ntiles + 1, 256), 256, 0, st, ptr,
             n_seg, ntiles, tile_seg);
   SB_LAUNCH((expand_ptr_kernel<I, N, V>), (unsigned)ntiles, kExBlock, 0, st, ptr,
-            (const int64_t *)tile_seg, nnz, col, vals, out_row, out_col, out_vals);
+            (const int64_t *)tile_seg, nnz, col, vals, out_row, out_col, out_vals, row_base);
 }
 
 // =====================================================================================
@@ -372,6 +374,8 @@ void expand_ptr(Workspace &ws, const N *ptr, int64_t n_seg, int64_t nnz, const I
 template <typename I, typename N, typename V>
 void to_csc_core(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const I *row, const I *col,
                  const V *vals, N *out_col_ptr, I *out_row, V *out_vals) {
+  // n = number of col_ptr segments: dims[0] for the reference layout (square assumption),
+  // m for the row-block variant used by the multi-GPU path
   using UI = typename std::make_unsigned<I>::type;
   cudaStream_t st = ws.stream();
   SB_REQUIRE(m <= n, SB200_ERR_BAD_ARG,
@@ -537,6 +541,62 @@ int sb200_csr_to_csc(int device, int64_t n, int64_t m, int64_t nnz, const void *
       expand_ptr<I, N, NoVal>(ws, (const N *)row_ptr, n, nnz, (const I *)nullptr,
                               (const NoVal *)nullptr, rows, (I *)nullptr, (NoVal *)nullptr);
       to_csc_core<I, N, V>(ws, n, m, nnz, rows, (const I *)col, (const V *)vals,
+                           (N *)out_col_ptr, (I *)out_row, (V *)out_vals);
+    });
+  });
+}
+
+// ---- row-block variants for the multi-GPU path ----
+
+int sb200_coo_to_csr_block(int device, int64_t row_lo, int64_t n_local, int64_t m, int64_t nnz,
+                           const void *row, const void *col, const void *vals,
+                           void *out_row_ptr, void *out_col, void *out_vals, int id_type,
+                           int nnz_type, int val_type, void *stream) {
+  return guarded(device, [&] {
+    SB_REQUIRE(row_lo >= 0 && n_local >= 0 && m >= 0 && nnz >= 0 && out_row_ptr,
+               SB200_ERR_BAD_ARG, "bad argument");
+    SB_REQUIRE(nnz == 0 || (row && col && out_col), SB200_ERR_BAD_ARG, "null array");
+    Workspace ws(device, (cudaStream_t)stream);
+    const bool hv = vals != nullptr && out_vals != nullptr && val_type != SB200_VOID;
+    dispatch_inv(id_type, nnz_type, val_type, hv, [&](auto I_, auto N_, auto V_) {
+      using I = decltype(I_);
+      using N = decltype(N_);
+      using V = decltype(V_);
+      unsigned flags[2];
+      build_ptr_and_copy<I, N, V>(ws, (const I *)row, (const I *)col, (const V *)vals, nnz,
+                                  n_local, (N *)out_row_ptr, (I *)out_col, (V *)out_vals, flags,
+                                  (I)row_lo);
+      bool need_sort = flags[1] != 0;
+      if (flags[0])
+        need_sort =
+            !compressed_check<I, N, V>(ws, (const N *)out_row_ptr, (const I *)out_col, n_local);
+      if (need_sort)
+        compressed_sort_inplace<I, N, V>(ws, (const N *)out_row_ptr, (I *)out_col,
+                                         (V *)out_vals, n_local, m, nnz);
+    });
+  });
+}
+
+int sb200_csr_to_csc_block(int device, int64_t row_lo, int64_t n_local, int64_t m, int64_t nnz,
+                           const void *row_ptr, const void *col, const void *vals,
+                           void *out_col_ptr, void *out_row, void *out_vals, int id_type,
+                           int nnz_type, int val_type, void *stream) {
+  return guarded(device, [&] {
+    SB_REQUIRE(row_lo >= 0 && n_local >= 0 && m >= 0 && nnz >= 0 && row_ptr && out_col_ptr,
+               SB200_ERR_BAD_ARG, "bad argument");
+    SB_REQUIRE(nnz == 0 || (col && out_row), SB200_ERR_BAD_ARG, "null array");
+    Workspace ws(device, (cudaStream_t)stream);
+    const bool hv = vals != nullptr && out_vals != nullptr && val_type != SB200_VOID;
+    dispatch_inv(id_type, nnz_type, val_type, hv, [&](auto I_, auto N_, auto V_) {
+      using I = decltype(I_);
+      using N = decltype(N_);
+      using V = decltype(V_);
+      I *rows = ws.alloc<I>(nnz);
+      expand_ptr<I, N, NoVal>(ws, (const N *)row_ptr, n_local, nnz, (const I *)nullptr,
+                              (const NoVal *)nullptr, rows, (I *)nullptr, (NoVal *)nullptr,
+                              (I)row_lo);
+      // col_ptr gets m+1 entries here (one per global column)
+      to_csc_core<I, N, V>(ws, m, m, nnz, rows, (const I *)col, (const V *)vals,
                            (N *)out_col_ptr, (I *)out_row, (V *)out_vals);
     });
   });

@@ -25,7 +25,9 @@ SYMBOLS = [
     "sb200_csr_to_coo", "sb200_coo_to_csc", "sb200_csr_to_csc", "sb200_degree_reorder",
     "sb200_rcm_reorder", "sb200_rcm_last_stats", "sb200_rcm_last_cycles", "sb200_permute2d", "sb200_permute1d", "sb200_inverse_permutation",
     "sb200_degrees", "sb200_degree_distribution", "sb200_partition_rows", "sb200_launch_count",
-    "sb200_reset_launch_count",
+    "sb200_reset_launch_count", "sb200_coo_to_csr_block", "sb200_csr_to_csc_block",
+    "sb200_exclusive_scan", "sb200_rank_keys", "sb200_max_degree", "sb200_degree_histogram",
+    "sb200_degree_rank_combine",
 ]
 
 
@@ -241,3 +243,64 @@ def partition_rows(n, nnz, row_ptr, parts):
     _check(load().sb200_partition_rows(_dev(row_ptr), _i64(n), _i64(nnz), _p(row_ptr),
                                        _DT[row_ptr.dtype], ctypes.c_int(parts), bounds, _stream()))
     return list(bounds)
+
+
+# ------------------------------------------------------------------ multi-GPU building blocks
+def coo_to_csr_block(row_lo, n_local, m, row, col, vals=None, nnz_dtype=torch.int32):
+    nnz = row.numel()
+    row_ptr = torch.empty(n_local + 1, dtype=nnz_dtype, device=row.device)
+    ocol = torch.empty_like(col)
+    ovals = None if vals is None else torch.empty_like(vals)
+    _check(load().sb200_coo_to_csr_block(_dev(row), _i64(row_lo), _i64(n_local), _i64(m),
+                                         _i64(nnz), _p(row), _p(col), _p(vals), _p(row_ptr),
+                                         _p(ocol), _p(ovals), _DT[row.dtype], _DT[nnz_dtype],
+                                         _vt(vals), _stream()))
+    return row_ptr, ocol, ovals
+
+
+def csr_to_csc_block(row_lo, n_local, m, row_ptr, col, vals=None):
+    nnz = col.numel()
+    col_ptr = torch.empty(m + 1, dtype=row_ptr.dtype, device=col.device)
+    orow = torch.empty_like(col)
+    ovals = None if vals is None else torch.empty_like(vals)
+    _check(load().sb200_csr_to_csc_block(_dev(col), _i64(row_lo), _i64(n_local), _i64(m),
+                                         _i64(nnz), _p(row_ptr), _p(col), _p(vals), _p(col_ptr),
+                                         _p(orow), _p(ovals), _DT[col.dtype], _DT[row_ptr.dtype],
+                                         _vt(vals), _stream()))
+    return col_ptr, orow, ovals
+
+
+def exclusive_scan(x):
+    out = torch.empty(x.numel() + 1, dtype=x.dtype, device=x.device)
+    _check(load().sb200_exclusive_scan(_dev(x), _i64(x.numel()), _p(x), _p(out), _DT[x.dtype],
+                                       _stream()))
+    return out
+
+
+def rank_keys(keys, key_bound):
+    out = torch.empty_like(keys)
+    _check(load().sb200_rank_keys(_dev(keys), _i64(keys.numel()), _p(keys), _i64(key_bound),
+                                  _p(out), _DT[keys.dtype], _stream()))
+    return out
+
+
+def max_degree(n, row_ptr):
+    out = ctypes.c_int64(0)
+    _check(load().sb200_max_degree(_dev(row_ptr), _i64(n), _p(row_ptr), _DT[row_ptr.dtype],
+                                   ctypes.byref(out), _stream()))
+    return out.value
+
+
+def degree_histogram(n, row_ptr, nbins):
+    out = torch.empty(nbins, dtype=torch.int64, device=row_ptr.device)
+    _check(load().sb200_degree_histogram(_dev(row_ptr), _i64(n), _p(row_ptr), _DT[row_ptr.dtype],
+                                         _i64(nbins), _p(out), _stream()))
+    return out
+
+
+def degree_rank_combine(n, row_ptr, local_rank, offset, flip_from=-1):
+    out = torch.empty_like(local_rank)
+    _check(load().sb200_degree_rank_combine(_dev(row_ptr), _i64(n), _p(row_ptr), _p(local_rank),
+                                            _p(offset), _i64(flip_from), _p(out),
+                                            _DT[local_rank.dtype], _DT[row_ptr.dtype], _stream()))
+    return out

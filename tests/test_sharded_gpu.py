@@ -1,0 +1,92 @@
+"""GPU tests of the multi-GPU building blocks.
+
+* single GPU: the block kernels (sb200_coo_to_csr_block, sb200_csr_to_csc_block,
+  sb200_rank_keys, sb200_exclusive_scan, degree histogram / combine) against numpy / the oracle;
+* >= 2 GPUs: tests/sharded_gpu_worker.py under torchrun + NCCL, sharded operators bit-equal to
+  the single-GPU operators (skipped on a 1-GPU box; `gpurun --gpus 2` runs it)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import cpu_ops
+import graphs
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def sb():
+    from sparsebase_b200 import lib
+    lib.load()
+    return lib
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def eq(t, a):
+    return t is not None and np.array_equal(t.cpu().numpy(), np.asarray(a))
+
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_block_kernels_match_the_cpu_stand_in(sb, parts):
+    n, r, c = graphs.rmat(11, 8, seed=31)
+    vals = graphs.vals_for(len(r), seed=2)
+    rp = graphs.csr_of(n, r, c)
+    nnz = len(r)
+    bounds = sb.partition_rows(n, nnz, dev(rp), parts)
+    assert bounds == cpu_ops.partition_rows(n, nnz, torch.from_numpy(rp), parts)
+    for k in range(parts):
+        lo, hi = bounds[k], bounds[k + 1]
+        a, b = int(rp[lo]), int(rp[hi])
+        t = torch.from_numpy
+        got = sb.coo_to_csr_block(lo, hi - lo, n, dev(r[a:b]), dev(c[a:b]), dev(vals[a:b]))
+        exp = cpu_ops.coo_to_csr_block(lo, hi - lo, n, t(r[a:b].copy()), t(c[a:b].copy()),
+                                       t(vals[a:b].copy()))
+        assert all(eq(g, e.numpy()) for g, e in zip(got, exp)), ("coo_to_csr_block", k)
+        lrp = (rp[lo:hi + 1] - rp[lo]).astype(np.int32)
+        got = sb.csr_to_csc_block(lo, hi - lo, n, dev(lrp), dev(c[a:b]), dev(vals[a:b]))
+        exp = cpu_ops.csr_to_csc_block(lo, hi - lo, n, t(lrp), t(c[a:b].copy()), t(vals[a:b].copy()))
+        assert all(eq(g, e.numpy()) for g, e in zip(got, exp)), ("csr_to_csc_block", k)
+        md = sb.max_degree(hi - lo, dev(lrp))
+        assert md == cpu_ops.max_degree(hi - lo, t(lrp))
+        assert eq(sb.degree_histogram(hi - lo, dev(lrp), md + 1),
+                  cpu_ops.degree_histogram(hi - lo, t(lrp), md + 1).numpy())
+        local = sb.degree_reorder(hi - lo, dev(lrp), True)
+        assert eq(local, cpu_ops.degree_reorder(hi - lo, t(lrp), True).numpy())
+        off = np.arange(md + 1, dtype=np.int64) * 3 + 7
+        for flip in (-1, n - 1):
+            assert eq(sb.degree_rank_combine(hi - lo, dev(lrp), local, dev(off), flip),
+                      cpu_ops.degree_rank_combine(hi - lo, t(lrp), local.cpu(), t(off), flip).numpy())
+
+
+def test_rank_keys_and_scan(sb):
+    rng = np.random.default_rng(3)
+    for cnt, bound in ((1, 5), (1000, 1 << 20), (100003, 1 << 27)):
+        keys = rng.choice(bound, size=cnt, replace=False).astype(np.int32)
+        exp = np.empty(cnt, np.int32)
+        exp[np.argsort(keys)] = np.arange(cnt, dtype=np.int32)
+        assert eq(sb.rank_keys(dev(keys), bound), exp)
+    for dt in (np.int32, np.int64):
+        x = rng.integers(0, 50, size=70001).astype(dt)
+        assert eq(sb.exclusive_scan(dev(x)), np.concatenate([[0], np.cumsum(x)]).astype(dt))
+
+
+@pytest.mark.parametrize("graph,scale", [("rmat", 15), ("er", 16)])
+def test_sharded_operators_nccl(graph, scale):
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    world = 2 if ngpu < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29533",
+           os.path.join(ROOT, "tests", "sharded_gpu_worker.py"), "--graph", graph, "--scale",
+           str(scale)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "SHARDED OK" in r.stdout, r.stdout[-3000:] + r.stderr[-5000:]
