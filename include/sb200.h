@@ -147,8 +147,9 @@ int sb200_rcm_reorder(int device, int64_t n, int64_t nnz, const void *row_ptr, c
  * h_out4 = {levels walked by the persistent single-CTA kernel, levels done with grid-wide
  * kernels, number of BFS traversals, number of non-trivial connected components}. */
 int sb200_rcm_last_stats(int64_t *h_out4);
-/* SM-cycle counters of the narrow regime's per-level phases {load, claim, check, finalize,
- * write, -, -, -} accumulated by CTA 0 (profiling aid). */
+/* SM-cycle counters of the narrow regime's per-level phases {seek, claim, barrier 1, recheck,
+ * compaction, count exchange (barrier 2), sibling sort + queue write, degree rescan}
+ * accumulated by CTA 0 (profiling aid). */
 int sb200_rcm_last_cycles(int64_t *h_out8);
 
 /* ---- applying a permutation ---- */

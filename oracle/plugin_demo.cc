@@ -8,10 +8,10 @@
 // results.  Built into oracle/_ref/plugin_demo by `make -C oracle ref` (development container,
 // where /root/reference is mounted); the binary travels to the GPU box with the snapshot and
 // tests/test_plugin_demo.py runs it there.
-#include <malloc.h>
-
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <new>
 #include <random>
 #include <vector>
 
@@ -23,6 +23,17 @@
 #include "sparsebase/utils/logger.h"
 // the plugin (includes the reference's CUDA format headers)
 #include "../sparsebase_b200/host/plugin/sb200_sparsebase_plugin.h"
+
+// degree_reorder.cc:41-45 reads and writes mr[n], one element past `new IDType[n]()`.  Like
+// oracle/ref_harness.cc, give every array allocation of this test program zeroed slack so that
+// the stray slot has the value 0 deterministically instead of corrupting the heap.
+void *operator new[](std::size_t sz) {
+  void *p = std::calloc(1, sz + 64);
+  if (!p) throw std::bad_alloc();
+  return p;
+}
+void operator delete[](void *p) noexcept { std::free(p); }
+void operator delete[](void *p, std::size_t) noexcept { std::free(p); }
 
 using namespace sparsebase;
 using I = int;
@@ -194,7 +205,6 @@ static void run_case(const char *name, Coo c, context::CPUContext &cpu, context:
 }
 
 int main() {
-  mallopt(M_MMAP_THRESHOLD, 4096);  // degree_reorder.cc:41-45 writes mr[n]
   utils::Logger::set_level(utils::LOG_LVL_NONE);
   context::CPUContext cpu;
   context::CUDAContext gpu(0);

@@ -164,7 +164,8 @@ struct InPlaceLoader {
   const I *idx;
   const V *vals;
   __device__ int64_t seg_base(int64_t r) const { return (int64_t)ptr[r]; }
-  __device__ I key(int64_t p) const { return idx[p]; }
+  __device__ I raw_key(int64_t p) const { return idx[p]; }
+  __device__ I map_key(I c) const { return c; }
   __device__ V val(int64_t p) const { return vals[p]; }
 };
 

@@ -27,7 +27,7 @@
 namespace sb200 {
 
 constexpr unsigned kUnvisited = 0xffffffffu;
-constexpr int kNwBlock = 1024;
+constexpr int kNwBlock = 512;
 constexpr int kNwWarps = kNwBlock / 32;
 constexpr int kNwGroupCap = 96;     // max degree in a CM frontier (bounds sibling groups)
 constexpr int64_t kBulkThreshold = 1 << 15;  // resets / inversions larger than this go wide
@@ -60,6 +60,7 @@ struct RcmState {
   int32_t next_phase_after_reset;
   int32_t pad;
   int64_t frontier_maxdeg;  // max degree over the current frontier (for the narrow caps)
+  int64_t key_base;    // peripheral BFS: expansion slots of all earlier levels (monotone claim keys)
   int64_t inv_qst, inv_end;  // pending bulk inversion
   int64_t stat_levels_narrow, stat_levels_wide, stat_bfs, stat_components;
   int64_t cyc[8];  // narrow-level phase cycle counters (CTA 0): load, claim, check, finalize, write
@@ -114,67 +115,66 @@ __device__ __forceinline__ void warp_expand(int64_t xs, unsigned d, Fn &&f) {
 //
 // A single SM cannot issue the ~3 scattered L2 accesses per edge of a 4096-wide level fast
 // enough (measured: 36 us per level, LSU-bound), so the level is split over the CTAs of one
-// cluster (16 where the device allows it, else 8): CTA k owns the k-th contiguous share of the
-// frontier, claims with atomicMin in L2, and the CTAs exchange their counts through
-// distributed shared memory; cluster barriers (~0.2 us) replace grid-wide ones.
+// cluster (16 where the device allows it, else 8).  Every CTA keeps ITS share of the frontier
+// in shared memory from one level to the next: the vertices it discovers (already sorted,
+// with their adjacency extents) are its share of the next level, so a level needs no global
+// re-read and only two cluster barriers:
+//     claims (atomicMin in L2)            -> barrier 1 ->
+//     recheck, compaction, sibling sort   -> exchange of the per-CTA counts (barrier 2)
+// The global queue is still written every level (it is the result), but nobody waits for it.
+// Shares drift apart over time (a BFS starts with everything in CTA 0); when the largest
+// share exceeds twice the even share, or shared memory, the CTAs re-split the frontier evenly
+// from the global queue (cl_reload, one more barrier).
 // All CTAs run the same state machine on replicated state, so control flow is uniform.
 // ------------------------------------------------------------------------------------
 constexpr int kClMax = 16;
+// expansion slots (and provisional / final winners) per CTA and level; 8-byte ids get fewer so
+// that the staging arrays stay inside the 227 KB of shared memory
+constexpr int kEl = 4096;
+constexpr int kEl64 = 3072;
+template <typename I>
+constexpr int cl_el() {
+  return sizeof(I) == 4 ? kEl : kEl64;
+}
 constexpr int kFl = 1024;  // frontier vertices per CTA and level
-constexpr int kEl = 4096;  // expansion slots per CTA and level (<= 4 per thread)
-constexpr int kClSpt = kEl / kNwBlock;
+constexpr int kClBatch = 4;  // 32-slot rounds whose loads are in flight together
 
 template <typename I>
 struct ClSmem {
+  // this CTA's share of the current frontier: vertex, adjacency start, degree
   I F[kFl];
   int64_t Fx[kFl];
   unsigned Fd[kFl];
-  unsigned off[kFl + 1];
-  I cv[kEl];
-  unsigned ci[kEl];
-  unsigned cd[kEl];
-  int64_t cx[kEl];
+  // provisional winners of sweep 1, one region per warp (region base = prefix of wslot[])
+  I pv[cl_el<I>()];
+  unsigned pkey[cl_el<I>()];  // claim key; 0 after sweep 2 when the claim lost
+  unsigned pi[cl_el<I>()];    // local index of the parent in F
+  int64_t px[cl_el<I>()];     // adjacency start / degree of the claimed vertex (filled by sweep 2)
+  unsigned pd[cl_el<I>()];
+  // final winners in slot order
+  I cv[cl_el<I>()];
+  unsigned ci[cl_el<I>()];
+  unsigned cd[cl_el<I>()];
+  int64_t cx[cl_el<I>()];
   unsigned long long xch[2][kClMax][4];
   unsigned long long mine[4];
   unsigned wtot[kNwWarps + 2];
+  unsigned wslot[kNwWarps];  // expansion slots of each warp's part of the share
+  unsigned wprov[kNwWarps];
+  unsigned wwin[kNwWarps];
+  unsigned wmax[kNwWarps];
+  unsigned wsum[kNwWarps];
   unsigned scratch[34];
   unsigned long long red[kNwWarps];
+  int fl;        // share size
+  long long fb;  // global frontier position of F[0]
+  unsigned sbase;  // expansion slots of the shares of the lower-ranked CTAs (this level)
+  // replicated: largest number of expansion slots of any share, slots of the whole level;
+  // need_reload = 1: the shares must be re-split from the global queue
+  unsigned long long max_slots;
+  unsigned long long level_slots;
+  int need_reload;
   RcmState S;
-};
-
-template <typename I>
-struct ClCursor {
-  int i;
-  unsigned j, rem;
-  int64_t p;
-  __device__ __forceinline__ void seek(const ClSmem<I> &s, int f, unsigned slot) {
-    int lo = 0, hi = f;  // last i with off[i] <= slot (its degree is non-zero)
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s.off[mid] <= slot)
-        lo = mid;
-      else
-        hi = mid;
-    }
-    i = lo;
-    j = slot - s.off[lo];
-    rem = s.Fd[lo] - j;
-    p = s.Fx[lo] + j;
-  }
-  __device__ __forceinline__ void next(const ClSmem<I> &s, int f) {
-    p++;
-    j++;
-    if (--rem == 0) {
-      do {
-        i++;
-      } while (i < f && s.Fd[i] == 0);
-      if (i < f) {
-        rem = s.Fd[i];
-        p = s.Fx[i];
-        j = 0;
-      }
-    }
-  }
 };
 
 }  // namespace sb200
@@ -200,24 +200,108 @@ __device__ __forceinline__ void cl_exchange(cg::cluster_group &cluster, ClSmem<I
   par ^= 1;
 }
 
+// Warp w expands the share's vertices [fl*w/W, fl*(w+1)/W).
+__device__ __forceinline__ int cl_part_begin(int fl, unsigned w) {
+  return (int)(((long long)fl * w) / kNwWarps);
+}
+
+// Per-warp expansion-slot totals of the share F[0..fl) -> s.wslot[]; returns the CTA total.
+// Contains __syncthreads().
+template <typename I>
+__device__ __forceinline__ unsigned cl_count_slots(ClSmem<I> &s, int fl) {
+  const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
+  unsigned sum = 0;
+  for (int i = cl_part_begin(fl, wid) + (int)lane; i < cl_part_begin(fl, wid + 1); i += 32)
+    sum += s.Fd[i];
+  sum = warp_reduce_sum(sum);
+  if (lane == 0) s.wslot[wid] = sum;
+  __syncthreads();
+  unsigned total = 0;
+#pragma unroll
+  for (int w = 0; w < kNwWarps; w++) total += s.wslot[w];
+  return total;
+}
+
+// Re-split the frontier queue[lvl_begin, lvl_end) evenly over the CTAs (also the way a BFS
+// starts and the way the kernel resumes after a host-driven step).  Contains cluster barriers.
+template <typename I, typename N>
+__device__ void cl_reload(cg::cluster_group &cluster, const RcmArgs<I, N> &a, ClSmem<I> &s,
+                          const I *queue, int &par) {
+  const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
+  cluster.sync();  // every CTA's queue writes of the previous level are visible
+  const int64_t f = s.S.lvl_end - s.S.lvl_begin;
+  const int64_t max_share = (f + C - 1) / C;
+  int fl = 0;
+  long long fb = 0;
+  unsigned total = 0;
+  if (max_share <= kFl) {
+    fb = f * rank / C;
+    fl = (int)(f * (rank + 1) / C - fb);
+    for (int i = threadIdx.x; i < fl; i += kNwBlock) {
+      const I v = __ldcg(queue + s.S.lvl_begin + fb + i);
+      const int64_t xs = (int64_t)a.xadj[v];
+      s.F[i] = v;
+      s.Fx[i] = xs;
+      s.Fd[i] = (unsigned)((int64_t)a.xadj[v + 1] - xs);
+    }
+    __syncthreads();
+    total = cl_count_slots(s, fl);
+  }
+  if (threadIdx.x == 0) {
+    s.fl = fl;
+    s.fb = fb;
+    s.mine[0] = max_share <= kFl ? total : (unsigned long long)cl_el<I>() + 1;  // too wide: go wide
+    s.mine[1] = s.mine[2] = s.mine[3] = 0;
+  }
+  cl_exchange(cluster, s, par);
+  unsigned long long mx = 0, sum = 0, below = 0;
+  for (unsigned k = 0; k < C; k++) {
+    const unsigned long long tk = s.xch[par ^ 1][k][0];
+    mx = tk > mx ? tk : mx;
+    sum += tk;
+    below += k < rank ? tk : 0ull;
+  }
+  if (threadIdx.x == 0) {
+    s.max_slots = mx;
+    s.level_slots = sum;
+    s.sbase = (unsigned)below;
+    s.need_reload = 0;
+  }
+  __syncthreads();
+}
+
 // One BFS level across the cluster.  Returns the number of newly reached vertices (cluster
 // total), or -1 when the level has to be done by the wide path (nothing modified then).
 // On return *next_maxdeg holds the maximum degree among the new vertices.
+//
+//   sweep 1   every warp walks the concatenated adjacency lists of its part of the share 32
+//             slots at a time (kClBatch rounds in flight), claims with atomicMin and appends
+//             the claims that were the minimum when they landed to its provisional list
+//   barrier 1 all claims of the level have landed
+//   sweep 2   every warp re-reads the marks of its provisional claims (a claim survived iff
+//             the mark still equals its key), fetches the winners' adjacency extents in the
+//             same round trip and marks them visited
+//   compaction into slot order, counts exchanged through distributed shared memory (barrier 2)
+//   ordering  slot order (peripheral) or per-parent (degree, id) order (CM), written to the
+//             global queue and -- unless the shares drifted apart -- kept as the next share
 template <typename I, typename N, bool CM>
 __device__ long long cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a, ClSmem<I> &s,
                               I *queue, int &par, unsigned cur_maxdeg, unsigned *next_maxdeg) {
   const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
   const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
   const int64_t f = s.S.lvl_end - s.S.lvl_begin;
-  const int64_t fb = f * rank / C, fe = f * (rank + 1) / C;
-  const int fl = (int)(fe - fb);
-  // uniform feasibility checks (every CTA evaluates the same numbers)
-  const int64_t max_share = (f + C - 1) / C;
-  if (max_share > kFl) return -1;
+  // uniform feasibility checks (every CTA evaluates the same replicated numbers)
+  if (s.max_slots > (unsigned long long)cl_el<I>()) return -1;
   if (CM && cur_maxdeg > (unsigned)kNwGroupCap) return -1;
-  const int jbits = bits_for_dev(cur_maxdeg);
-  if (!CM && bits_for_dev((unsigned long long)f) + jbits > 31) return -1;
-  const bool need_check = (unsigned long long)max_share * cur_maxdeg > (unsigned long long)kEl;
+  // Claim keys grow from level to level (CM: queue position of the parent; peripheral: running
+  // expansion-slot number of the BFS), so a vertex reached earlier always holds a SMALLER mark
+  // than any later claim: visited vertices need no separate "visited" store, and barrier 2 has
+  // no global writes to wait for.
+  if (!CM && (unsigned long long)s.S.key_base + s.level_slots >= 0xfffffff0ull) return -1;
+  const unsigned kb = CM ? (unsigned)s.S.lvl_begin : (unsigned)s.S.key_base + s.sbase;
+  (void)f;
+  const int fl = s.fl;
+  const long long fb = s.fb;
   long long t0 = clock64(), t1;
 #define SB_TICK(slot)                                   \
   do {                                                  \
@@ -226,145 +310,167 @@ __device__ long long cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a
     t0 = t1;                                            \
   } while (0)
 
-  // ---- my share of the frontier: vertex, adjacency start, degree ----
-  for (int i = threadIdx.x; i < fl; i += kNwBlock) {
-    const I v = queue[s.S.lvl_begin + fb + i];
-    const int64_t xs = (int64_t)a.xadj[v];
-    s.F[i] = v;
-    s.Fx[i] = xs;
-    s.Fd[i] = (unsigned)((int64_t)a.xadj[v + 1] - xs);
-  }
-  __syncthreads();
-  // exclusive scan of the degrees -> local expansion slot offsets
-  unsigned d = (int)threadIdx.x < fl ? s.Fd[threadIdx.x] : 0u;
-  unsigned total;
-  const unsigned ex = block_exclusive_scan(d, s.scratch, &total);
-  if ((int)threadIdx.x < fl) s.off[threadIdx.x] = ex;
-  __syncthreads();
-  if (need_check) {  // rare: agree cluster-wide that every share fits
-    if (threadIdx.x == 0) {
-      s.mine[0] = total;
-      s.mine[1] = s.mine[2] = s.mine[3] = 0;
-    }
-    cl_exchange(cluster, s, par);
-    unsigned long long mx = 0;
-    for (unsigned k = 0; k < C; k++) mx = s.xch[par ^ 1][k][0] > mx ? s.xch[par ^ 1][k][0] : mx;
-    if (mx > (unsigned long long)kEl) return -1;
-  }
-
-  const unsigned spt = (total + kNwBlock - 1) / kNwBlock;  // <= kClSpt
-  const unsigned s0 = threadIdx.x * spt;
-  const unsigned s1 = s0 + spt < total ? s0 + spt : total;
-  ClCursor<I> start;
-  start.i = 0;
-  start.j = 0;
-  start.rem = 0;
-  start.p = 0;
-  if (s0 < total) start.seek(s, fl, s0);
+  unsigned pbase = 0;  // my warp's provisional region
+#pragma unroll
+  for (int w = 0; w < kNwWarps; w++) pbase += (unsigned)w < wid ? s.wslot[w] : 0u;
+  unsigned pcount = 0;
+  unsigned goff = pbase;  // expansion-slot number (inside this CTA's share) of the group's slot 0
   SB_TICK(0);
 
   // ---- sweep 1: claims.  key orders (global frontier position[, adjacency index]) ----
-  I v[kClSpt];
-  unsigned key[kClSpt];
-  unsigned prov = 0;  // slots that were the minimum when their claim landed
-  {
-    ClCursor<I> cur = start;
-#pragma unroll
-    for (int u = 0; u < kClSpt; u++) {
-      if (s0 + u < s1) {
-        v[u] = a.adj[cur.p];
-        const unsigned gi = (unsigned)(fb + cur.i);
-        key[u] = CM ? gi + 1u : ((gi << jbits) | cur.j) + 1u;
-        cur.next(s, fl);
-      }
+  const int vb = cl_part_begin(fl, wid), ve = cl_part_begin(fl, wid + 1);
+  for (int g = vb; g < ve; g += 32) {
+    const int i = g + (int)lane;
+    int64_t xs = 0;
+    unsigned d = 0;
+    if (i < ve) {
+      xs = s.Fx[i];
+      d = s.Fd[i];
     }
-    unsigned old[kClSpt];
+    const unsigned incl = warp_inclusive_scan(d);
+    const unsigned excl = incl - d;
+    const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
+    for (unsigned b0 = 0; b0 < tot; b0 += 32 * kClBatch) {
+      I v[kClBatch];
+      unsigned key[kClBatch], own[kClBatch], old[kClBatch];
+      bool valid[kClBatch];
 #pragma unroll
-    for (int u = 0; u < kClSpt; u++)
-      if (s0 + u < s1) old[u] = atomicMin(&a.mark[v[u]], key[u]);
+      for (int u = 0; u < kClBatch; u++) {
+        const unsigned sl = b0 + u * 32 + lane;
+        unsigned lo = 0;  // number of lanes whose inclusive end <= sl  == owner lane
 #pragma unroll
-    for (int u = 0; u < kClSpt; u++) {
-      if (s0 + u < s1 && old[u] > key[u]) {
-        prov |= 1u << u;
-        // a provisional winner's adjacency extent is read in the finalize phase: start the
-        // DRAM access now so that it overlaps the barrier and the check phase
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.xadj + v[u]));
-      }
-    }
-  }
-  cluster.sync();
-  SB_TICK(1);
-
-  // ---- sweep 2: which provisional winners survived? ----
-  unsigned wbits = 0, wcount = 0;
-  {
-    unsigned m[kClSpt];
-#pragma unroll
-    for (int u = 0; u < kClSpt; u++)
-      if ((prov >> u) & 1u) m[u] = __ldcg(&a.mark[v[u]]);
-#pragma unroll
-    for (int u = 0; u < kClSpt; u++) {
-      if (((prov >> u) & 1u) && m[u] == key[u]) {
-        wbits |= 1u << u;
-        wcount++;
-      }
-    }
-  }
-  unsigned c_local;
-  unsigned pos = block_exclusive_scan(wcount, s.scratch, &c_local);
-  // ---- ordered (slot order) compaction of my winners into shared memory ----
-  {
-    ClCursor<I> cur = start;
-#pragma unroll
-    for (int u = 0; u < kClSpt; u++) {
-      if (s0 + u < s1) {
-        if ((wbits >> u) & 1u) {
-          s.cv[pos] = v[u];
-          s.ci[pos] = (unsigned)cur.i;
-          pos++;
+        for (int step = 16; step > 0; step >>= 1) {
+          const unsigned val = __shfl_sync(0xffffffffu, incl, (lo + step - 1) & 31);
+          if (val <= sl) lo += step;
         }
-        cur.next(s, fl);
+        const unsigned j = lo & 31;
+        const int64_t xs_j = __shfl_sync(0xffffffffu, xs, j);
+        const unsigned excl_j = __shfl_sync(0xffffffffu, excl, j);
+        valid[u] = sl < tot;
+        own[u] = (unsigned)g + j;
+        key[u] = CM ? kb + (unsigned)(fb + g + j) + 1u : kb + goff + sl + 1u;
+        if (valid[u]) v[u] = a.adj[xs_j + (int64_t)(sl - excl_j)];
+      }
+#pragma unroll
+      for (int u = 0; u < kClBatch; u++)
+        if (valid[u]) old[u] = atomicMin(&a.mark[v[u]], key[u]);
+#pragma unroll
+      for (int u = 0; u < kClBatch; u++) {
+        const bool prov = valid[u] && old[u] > key[u];
+        const unsigned bal = __ballot_sync(0xffffffffu, prov);
+        if (prov) {
+          const unsigned at = pbase + pcount + __popc(bal & lanemask_lt());
+          s.pv[at] = v[u];
+          s.pkey[at] = key[u];
+          s.pi[at] = own[u];
+        }
+        pcount += __popc(bal);
       }
     }
+    goff += tot;
   }
-  __syncthreads();
+  SB_TICK(1);
+  cluster.sync();
   SB_TICK(2);
 
-  // ---- new vertices: mark visited, fetch their adjacency extent ----
-  const int c = (int)c_local;
-  unsigned mymax = 0;
-  for (int k = threadIdx.x; k < c; k += kNwBlock) {
-    const I w = s.cv[k];
-    const int64_t xs = (int64_t)a.xadj[w];
-    const int64_t xe = (int64_t)a.xadj[w + 1];
-    atomicExch(&a.mark[w], 0u);
-    s.cx[k] = xs;
-    const unsigned dg = (unsigned)(xe - xs);
-    s.cd[k] = dg;
-    mymax = dg > mymax ? dg : mymax;
+  // ---- sweep 2: which provisional claims survived?  (warp-local lists) ----
+  unsigned wins = 0, mymax = 0, mysum = 0;
+  for (unsigned k0 = 0; k0 < pcount; k0 += 32 * kClBatch) {
+    I v[kClBatch];
+    unsigned m[kClBatch];
+    N xs[kClBatch], xe[kClBatch];
+#pragma unroll
+    for (int u = 0; u < kClBatch; u++) {
+      const unsigned k = k0 + u * 32 + lane;
+      if (k < pcount) {
+        v[u] = s.pv[pbase + k];
+        m[u] = __ldcg(&a.mark[v[u]]);
+        xs[u] = a.xadj[v[u]];
+        xe[u] = a.xadj[v[u] + 1];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kClBatch; u++) {
+      const unsigned k = k0 + u * 32 + lane;
+      if (k < pcount) {
+        if (m[u] == s.pkey[pbase + k]) {
+          const unsigned dg = (unsigned)(xe[u] - xs[u]);
+          s.px[pbase + k] = (int64_t)xs[u];
+          s.pd[pbase + k] = dg;
+          mymax = dg > mymax ? dg : mymax;
+          mysum += dg;
+          wins++;
+        } else {
+          s.pkey[pbase + k] = 0u;
+        }
+      }
+    }
   }
+  wins = warp_reduce_sum(wins);
   mymax = warp_reduce_max(mymax);
-  if (lane == 0) s.wtot[wid] = mymax;
+  mysum = warp_reduce_sum(mysum);
+  if (lane == 0) {
+    s.wwin[wid] = wins;
+    s.wmax[wid] = mymax;
+    s.wsum[wid] = mysum;
+  }
+  SB_TICK(3);
   __syncthreads();
+  // ---- ordered compaction of the winners (warp regions are already in slot order) ----
+  unsigned wb = 0, c_local = 0;
+#pragma unroll
+  for (int w = 0; w < kNwWarps; w++) {
+    const unsigned cw = s.wwin[w];
+    wb += (unsigned)w < wid ? cw : 0u;
+    c_local += cw;
+  }
+  for (unsigned k0 = 0; k0 < pcount; k0 += 32) {
+    const unsigned k = k0 + lane;
+    const bool win = k < pcount && s.pkey[pbase + k] != 0u;
+    const unsigned bal = __ballot_sync(0xffffffffu, win);
+    if (win) {
+      const unsigned at = wb + __popc(bal & lanemask_lt());
+      s.cv[at] = s.pv[pbase + k];
+      s.ci[at] = s.pi[pbase + k];
+      s.cx[at] = s.px[pbase + k];
+      s.cd[at] = s.pd[pbase + k];
+    }
+    wb += __popc(bal);
+  }
   if (threadIdx.x == 0) {
-    unsigned mx = 0;
-    for (int w = 0; w < kNwWarps; w++) mx = s.wtot[w] > mx ? s.wtot[w] : mx;
+    unsigned mx = 0, sm = 0;
+#pragma unroll
+    for (int w = 0; w < kNwWarps; w++) {
+      mx = s.wmax[w] > mx ? s.wmax[w] : mx;
+      sm += s.wsum[w];
+    }
     s.mine[0] = c_local;
     s.mine[1] = mx;
-    s.mine[2] = s.mine[3] = 0;
+    s.mine[2] = sm;
+    s.mine[3] = 0;
   }
+  SB_TICK(4);
   cl_exchange(cluster, s, par);
-  long long cbase = 0, ctotal = 0;
-  unsigned nmax = 0;
-  for (unsigned k = 0; k < C; k++) {
-    const long long ck = (long long)s.xch[par ^ 1][k][0];
-    if (k < rank) cbase += ck;
-    ctotal += ck;
-    const unsigned mk = (unsigned)s.xch[par ^ 1][k][1];
-    nmax = mk > nmax ? mk : nmax;
+  const int c = (int)c_local;
+  // every warp reduces the C records with its first C lanes
+  unsigned ck = 0, mk = 0, sk = 0;
+  if (lane < C) {
+    ck = (unsigned)s.xch[par ^ 1][lane][0];
+    mk = (unsigned)s.xch[par ^ 1][lane][1];
+    sk = (unsigned)s.xch[par ^ 1][lane][2];
   }
+  const long long cbase = warp_reduce_sum(lane < rank ? ck : 0u);
+  const long long ctotal = warp_reduce_sum(ck);
+  const long long cmax = warp_reduce_max(ck);
+  const unsigned nmax = warp_reduce_max(mk);
+  const unsigned long long smax = warp_reduce_max(sk);
+  const unsigned sbase_next = warp_reduce_sum(lane < rank ? sk : 0u);
+  const unsigned long long slots_next = warp_reduce_sum(sk);
   *next_maxdeg = nmax;
-  SB_TICK(3);
+  // keep the shares where they are unless they have drifted too far apart (uniform decision)
+  const bool keep = cmax <= kFl && smax <= (unsigned long long)cl_el<I>() &&
+                    cmax <= 2 * ((ctotal + C - 1) / C) + 32;
+  SB_TICK(5);
 
   // ---- next frontier: slot order (peripheral) or (parent, degree, id) order (CM); the
   //      sibling groups of a parent never leave the CTA that owns the parent ----
@@ -372,8 +478,9 @@ __device__ long long cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a
   for (int k = threadIdx.x; k < c; k += kNwBlock) {
     int dst = k;
     const I w = s.cv[k];
+    const unsigned dg = s.cd[k];
     if (CM) {
-      const unsigned par_i = s.ci[k], dg = s.cd[k];
+      const unsigned par_i = s.ci[k];
       int rank_in = 0, left = 0;
       for (int q = k - 1; q >= 0 && s.ci[q] == par_i; q--) {
         left++;
@@ -384,11 +491,30 @@ __device__ long long cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a
       dst = k - left + rank_in;
     }
     queue[out0 + dst] = w;
+    if (keep) {  // c <= kFl
+      s.F[dst] = w;
+      s.Fx[dst] = s.cx[k];
+      s.Fd[dst] = dg;
+    }
     // the next level starts by reading this vertex's adjacency list: pull it towards L2 now
     asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + s.cx[k]));
   }
-  cluster.sync();  // the queue slice is complete and visible to every CTA
-  SB_TICK(4);
+  if (threadIdx.x == 0) {
+    if (!CM) s.S.key_base += (int64_t)s.level_slots;  // this level's slots are used up
+    if (keep) {
+      s.fl = c;
+      s.fb = cbase;
+      s.sbase = sbase_next;
+      s.max_slots = smax;
+      s.level_slots = slots_next;
+    } else {
+      s.need_reload = 1;
+    }
+  }
+  __syncthreads();
+  SB_TICK(6);
+  if (keep) cl_count_slots(s, c);  // ends with a barrier
+  SB_TICK(7);
 #undef SB_TICK
   return ctotal;
 }
@@ -405,6 +531,10 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
   if (threadIdx.x == 0) {
     s.S = *a.state;
     s.S.status = ST_RUNNING;
+    s.fl = 0;
+    s.fb = 0;
+    s.max_slots = 0;
+    s.need_reload = 1;  // nothing is resident yet: the first level splits the queue
   }
   __syncthreads();
   cur_maxdeg = (unsigned)s.S.frontier_maxdeg;
@@ -437,7 +567,7 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
           unvis[k] = false;
           isolated[k] = false;
           if (i < a.n) {
-            unvis[k] = __ldcg(&a.mark[i]) != 0u;
+            unvis[k] = __ldcg(&a.mark[i]) == kUnvisited;
             isolated[k] = a.xadj[i] == a.xadj[i + 1];
           }
         }
@@ -501,31 +631,36 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
       }
       cur_maxdeg = (unsigned)((int64_t)a.xadj[r + 1] - (int64_t)a.xadj[r]);
       if (threadIdx.x == 0) {
-        if (cm)
+        if (cm) {
           s.S.qst = s.S.qwp;
-        else
+        } else {
           s.S.rlevel = s.S.qlevel;
+          s.S.key_base = 0;
+        }
         s.S.lvl_begin = at;
         s.S.lvl_end = at + 1;
         s.S.prev_begin = at;
         s.S.depth = 0;
         s.S.phase = cm ? PH_CM_LEVEL : PH_PBFS_LEVEL;
         s.S.stat_bfs++;
+        s.need_reload = 1;  // the reload's barrier publishes the root to every CTA
       }
-      cluster.sync();  // the root is in the queue for every CTA
+      __syncthreads();
       continue;
     }
 
     if (phase == PH_PBFS_LEVEL || phase == PH_CM_LEVEL) {
       const int64_t f = s.S.lvl_end - s.S.lvl_begin;
       if (f == 0) {
-        __syncthreads();
+        cluster.sync();  // the queue is complete: the END phases read other CTAs' slices
         if (threadIdx.x == 0) s.S.phase = phase == PH_PBFS_LEVEL ? PH_PBFS_END : PH_CM_END;
         __syncthreads();
         continue;
       }
       long long c = -1;
       unsigned next_maxdeg = 0;
+      if (!a.force_wide && s.need_reload)
+        cl_reload<I, N>(cluster, a, s, phase == PH_PBFS_LEVEL ? a.Qp : a.Q, par);
       if (!a.force_wide)
         c = phase == PH_PBFS_LEVEL
                 ? cl_level<I, N, false>(cluster, a, s, a.Qp, par, cur_maxdeg, &next_maxdeg)
@@ -739,9 +874,10 @@ __global__ void rcm_wide_commit_kernel(const uint32_t *__restrict__ sorted, int6
 }
 
 template <typename I>
-__global__ void rcm_reset_kernel(const I *__restrict__ q, int64_t cnt, unsigned *__restrict__ mark) {
+__global__ void rcm_reset_kernel(const I *__restrict__ q, int64_t cnt, unsigned *__restrict__ mark,
+                                 unsigned value) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < cnt) mark[q[k]] = kUnvisited;
+  if (k < cnt) mark[q[k]] = value;
 }
 
 template <typename I>
@@ -894,6 +1030,10 @@ void rcm_impl(Workspace &ws, int64_t n, int64_t nnz, const N *xadj, const I *adj
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int cluster = kClMax;
+  if (const char *cs = getenv("SB200_RCM_CLUSTER")) {  // tuning aid: 1, 2, 4, 8 or 16
+    const int want = atoi(cs);
+    if (want >= 1 && want <= kClMax && (want & (want - 1)) == 0) cluster = want;
+  }
   for (; cluster >= 1; cluster >>= 1) {  // largest cluster the device can co-schedule
     cfg.gridDim = dim3(cluster, 1, 1);
     attr[0].val.clusterDim.x = cluster;
@@ -915,6 +1055,14 @@ void rcm_impl(Workspace &ws, int64_t n, int64_t nnz, const N *xadj, const I *adj
     if (S.status == ST_NEED_WIDE) {
       prepare_wide();
       const bool cm = S.phase == PH_CM_LEVEL;
+      {
+        // the cluster kernel leaves the (monotone) claim key in mark[] of every vertex it
+        // reached; the wide kernels use per-level keys and expect 0 = visited
+        const int64_t from = cm ? S.qst : 0, cnt = S.lvl_end - from;
+        if (cnt > 0)
+          SB_LAUNCH((rcm_reset_kernel<I>), (unsigned)ceil_div(cnt, 256), 256, 0, st,
+                    (const I *)(cm ? a.Q : a.Qp) + from, cnt, a.mark, 0u);
+      }
       // keep going wide while the frontier is far beyond the narrow capacity
       do {
         rcm_wide_level<I, N>(ws, a, w, S, cm);
@@ -922,7 +1070,7 @@ void rcm_impl(Workspace &ws, int64_t n, int64_t nnz, const N *xadj, const I *adj
     } else if (S.status == ST_NEED_RESET) {
       const int64_t cnt = S.lvl_end;
       SB_LAUNCH((rcm_reset_kernel<I>), (unsigned)ceil_div(cnt, 256), 256, 0, st, (const I *)a.Qp,
-                cnt, a.mark);
+                cnt, a.mark, kUnvisited);
     } else if (S.status == ST_NEED_INVERT) {
       const int64_t cnt = S.lvl_end - S.qst;
       SB_LAUNCH((rcm_invert_kernel<I>), (unsigned)ceil_div(cnt, 256), 256, 0, st, (const I *)a.Q,

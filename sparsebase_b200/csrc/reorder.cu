@@ -7,6 +7,8 @@
 //   sb200_permute1d           permute/permute_order_one.cc:17-37
 //   sb200_inverse_permutation bases/reorder_base.h:662-671
 //   sb200_partition_rows      (new) nnz-balanced row blocks for the multi-GPU path
+#include <limits>
+
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
@@ -125,18 +127,33 @@ void degree_reorder_impl(Workspace &ws, int64_t n, const N *row_ptr, bool ascend
 
 // ---------------------------------------------------------------- Permute2D
 // Old row i becomes new row j = row_order[i].  One coalesced pass over xadj scatters, per new
-// row, the source offset of its first entry and its length; the scan and the tile kernel then
-// read both arrays coalesced (no dependent irow -> xadj gathers inside the hot kernel).
+// row, the source offset of its first entry and its length; the scan and the gather kernels
+// then read both arrays coalesced (no dependent irow -> xadj gathers inside the hot kernels).
+// The same pass finds the longest row, which selects the gather kernel.
 template <typename I, typename N>
 __global__ void permute_prepare_kernel(const N *__restrict__ xadj, const I *__restrict__ row_order,
                                        int64_t n, int64_t *__restrict__ src_base,
-                                       N *__restrict__ new_len) {
+                                       N *__restrict__ new_len,
+                                       unsigned long long *__restrict__ max_len) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long len = 0;
   if (i < n) {
     const int64_t j = row_order ? (int64_t)row_order[i] : i;
     const N b = xadj[i], e = xadj[i + 1];
     src_base[j] = (int64_t)b;
     new_len[j] = e - b;
+    len = (unsigned long long)(e - b);
+  }
+  // one atomic per CTA, and only when it would raise the maximum (same-address atomics
+  // serialise in L2: one per warp cost 0.25 ms at 16.7 M rows)
+  __shared__ unsigned long long s_max[kMapBlock / 32];
+  len = warp_reduce_max(len);
+  if (lane_id() == 0) s_max[threadIdx.x >> 5] = len;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long mx = 0;
+    for (int w = 0; w < kMapBlock / 32; w++) mx = s_max[w] > mx ? s_max[w] : mx;
+    if (mx > *reinterpret_cast<volatile unsigned long long *>(max_len)) atomicMax(max_len, mx);
   }
 }
 
@@ -147,12 +164,132 @@ struct GatherLoader {
   const V *vals;
   const I *col_order;  // old col -> new col, or null
   __device__ int64_t seg_base(int64_t r) const { return src_base[r]; }
-  __device__ I key(int64_t p) const {
-    const I c = ld_stream(adj + p);
-    return col_order ? col_order[c] : c;
-  }
-  __device__ V val(int64_t p) const { return ld_stream(vals + p); }
+  // default cache policy on purpose: a gathered row shares its 32-byte sectors with the rows
+  // next to it in the SOURCE, which are gathered a little later (evict-first loads made HBM
+  // deliver those sectors twice)
+  __device__ I raw_key(int64_t p) const { return __ldg(adj + p); }
+  __device__ I map_key(I c) const { return col_order ? col_order[c] : c; }
+  __device__ V val(int64_t p) const { return __ldg(vals + p); }
 };
+
+// ---- matrices whose rows all have <= kShortRow entries (stencils, meshes).  One warp owns
+//      32 consecutive NEW rows per step.  Their entries are fetched in concatenated order
+//      (lane s reads the s-th entry of the 32-row batch: consecutive lanes read consecutive
+//      addresses inside a source row), staged in a 2 KB per-warp slice of shared memory,
+//      sorted by the lane that owns the row with a fixed compare-exchange network in
+//      registers, and written back as ONE contiguous, fully coalesced run -- the 32 rows are
+//      adjacent in the output.  No block barriers; three dependent loads per step (row records
+//      -> entries -> renumbered columns). ----
+constexpr int kShortRow = 8;
+constexpr int kSrBlock = 256;
+
+template <typename I, typename V>
+__device__ __forceinline__ void short_cex(I &ka, V &va, I &kb, V &vb) {
+  bool swap = kb < ka;
+  if constexpr (has_val<V>) swap = swap || (kb == ka && vb < va);
+  if (swap) {
+    const I tk = ka;
+    ka = kb;
+    kb = tk;
+    if constexpr (has_val<V>) {
+      const V tv = va;
+      va = vb;
+      vb = tv;
+    }
+  }
+}
+
+template <typename I, typename N, typename V>
+__global__ void __launch_bounds__(kSrBlock)
+    permute_short_rows_kernel(const int64_t *__restrict__ src_base,
+                              const N *__restrict__ out_ptr, const I *__restrict__ adj,
+                              const V *__restrict__ vals, const I *__restrict__ col_order,
+                              int64_t n, I *__restrict__ out_col, V *__restrict__ out_vals) {
+  using VR = typename std::conditional<has_val<V>, V, char>::type;
+  __shared__ I stage_k[kSrBlock / 32][32 * kShortRow];
+  __shared__ VR stage_v[kSrBlock / 32][has_val<V> ? 32 * kShortRow : 1];
+  const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
+  I *sk = stage_k[wid];
+  [[maybe_unused]] VR *sv = stage_v[wid];
+  const int64_t nbatches = (n + 31) >> 5;
+  const int64_t wstride = ((int64_t)gridDim.x * kSrBlock) >> 5;
+  for (int64_t bt = (((int64_t)blockIdx.x * kSrBlock) >> 5) + wid; bt < nbatches; bt += wstride) {
+    const int64_t j = (bt << 5) + lane;
+    int64_t ob = 0, p = 0;
+    unsigned len = 0;
+    if (j < n) {
+      ob = (int64_t)out_ptr[j];
+      len = (unsigned)((int64_t)out_ptr[j + 1] - ob);
+      p = src_base[j];
+    }
+    const int64_t ob0 = __shfl_sync(0xffffffffu, ob, 0);
+    const unsigned incl = warp_inclusive_scan(len);
+    const unsigned excl = incl - len;  // == ob - ob0 for the rows that exist
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    // ---- fetch in concatenated order ----
+    for (unsigned base = 0; base < total; base += 32) {
+      const unsigned sidx = base + lane;
+      unsigned owner = 0;  // number of lanes whose inclusive end <= sidx
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const unsigned val = __shfl_sync(0xffffffffu, incl, (owner + step - 1) & 31);
+        if (val <= sidx) owner += step;
+      }
+      owner &= 31;
+      const int64_t p_o = __shfl_sync(0xffffffffu, p, owner);
+      const unsigned ex_o = __shfl_sync(0xffffffffu, excl, owner);
+      if (sidx < total) {
+        const int64_t src = p_o + (int64_t)(sidx - ex_o);
+        I c = __ldg(adj + src);
+        if constexpr (has_val<V>) sv[sidx] = __ldg(vals + src);
+        if (col_order) c = col_order[c];
+        sk[sidx] = c;
+      }
+    }
+    __syncwarp();
+    // ---- the owning lane sorts its row in registers ----
+    I k[kShortRow];
+    [[maybe_unused]] VR v[kShortRow];
+#pragma unroll
+    for (int u = 0; u < kShortRow; u++) {
+      k[u] = std::numeric_limits<I>::max();  // padding sorts to the end
+      if constexpr (has_val<V>) v[u] = V(0);
+      if ((unsigned)u < len) {
+        k[u] = sk[excl + u];
+        if constexpr (has_val<V>) v[u] = sv[excl + u];
+      }
+    }
+    // Batcher odd-even merge sort for 8 keys (19 compare-exchanges)
+#define SB_CEX(a, b)                                          \
+  if constexpr (has_val<V>)                                   \
+    short_cex<I, V>(k[a], v[a], k[b], v[b]);                  \
+  else {                                                      \
+    NoVal nv1, nv2;                                           \
+    short_cex<I, NoVal>(k[a], nv1, k[b], nv2);                \
+  }
+    SB_CEX(0, 1) SB_CEX(2, 3) SB_CEX(4, 5) SB_CEX(6, 7)
+    SB_CEX(0, 2) SB_CEX(1, 3) SB_CEX(4, 6) SB_CEX(5, 7)
+    SB_CEX(1, 2) SB_CEX(5, 6)
+    SB_CEX(0, 4) SB_CEX(1, 5) SB_CEX(2, 6) SB_CEX(3, 7)
+    SB_CEX(2, 4) SB_CEX(3, 5)
+    SB_CEX(1, 2) SB_CEX(3, 4) SB_CEX(5, 6)
+#undef SB_CEX
+#pragma unroll
+    for (int u = 0; u < kShortRow; u++) {
+      if ((unsigned)u < len) {
+        sk[excl + u] = k[u];
+        if constexpr (has_val<V>) sv[excl + u] = v[u];
+      }
+    }
+    __syncwarp();
+    // ---- one contiguous run of the output ----
+    for (unsigned sidx = lane; sidx < total; sidx += 32) {
+      st_stream(out_col + ob0 + sidx, sk[sidx]);
+      if constexpr (has_val<V>) st_stream(out_vals + ob0 + sidx, (V)sv[sidx]);
+    }
+    __syncwarp();
+  }
+}
 
 template <typename I, typename N, typename V>
 void permute2d_impl(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const N *xadj,
@@ -161,10 +298,26 @@ void permute2d_impl(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const N *x
   cudaStream_t st = ws.stream();
   int64_t *src_base = ws.alloc<int64_t>(n + 1);
   N *new_len = ws.alloc<N>(n + 1);
+  unsigned long long *max_len = ws.alloc<unsigned long long>(1);
+  SB_CUDA(cudaMemsetAsync(max_len, 0, sizeof(unsigned long long), st));
   if (n > 0)
     SB_LAUNCH((permute_prepare_kernel<I, N>), map_grid(n), kMapBlock, 0, st, xadj, row_order, n,
-              src_base, new_len);
+              src_base, new_len, max_len);
   exclusive_scan<N>(ws, LoadFn<N>{new_len}, out_row_ptr, n);
+  if (n <= 0 || nnz <= 0) return;
+  unsigned long long h_max = 0;
+  SB_CUDA(cudaMemcpyAsync(&h_max, max_len, sizeof(h_max), cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  if (h_max <= (unsigned long long)kShortRow) {
+    // one 32-row batch per warp, CTAs in row order: neighbouring rows are in flight at the
+    // same time, so the sectors they share (20-byte rows in 32-byte sectors, nearby col_order
+    // entries) are fetched from HBM once.  (A grid-stride loop over a capped grid spreads the
+    // resident warps over distant row ranges and doubled the DRAM read traffic.)
+    SB_LAUNCH((permute_short_rows_kernel<I, N, V>), (unsigned)ceil_div(n, (int64_t)kSrBlock), kSrBlock,
+              0, st, (const int64_t *)src_base, (const N *)out_row_ptr, adj, vals, col_order, n,
+              out_col, out_vals);
+    return;
+  }
   GatherLoader<I, N, V> ld{src_base, adj, vals, col_order};
   segmented_sort<I, N, V>(ws, ld, (const N *)out_row_ptr, n, m, nnz, out_col, out_vals);
 }

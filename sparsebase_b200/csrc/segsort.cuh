@@ -3,7 +3,7 @@
 // Implements the arithmetic of the CSR / CSC constructor's per-row sort
 // (format/csr.cc:123-157, format/csc.cc:123-157) and, with a gathering loader, the whole of
 // PermuteOrderTwoCSR + that constructor sort (permute/permute_order_two.cc:64-77): each CTA
-// owns the segments that START inside one 2048-entry window of the OUTPUT layout, pulls their
+// owns the segments that START inside one 1024-entry window of the OUTPUT layout, pulls their
 // entries through the loader into shared memory (for Permute2D: old row located through the
 // inverted row order, column ids renumbered through col_order), sorts every segment on chip
 // and writes it to its final place.  Every nonzero is read once and written once.
@@ -28,38 +28,56 @@ constexpr int kSsLong = 1024;  // longest segment sorted on chip (must be >= kSs
 constexpr int kSsCap = kSsTile + kSsLong;
 constexpr int kSsEnum = 32;
 constexpr int kSsMaxMid = kSsCap / (kSsEnum + 1) + 1;
+constexpr int kSsScanPer = kSsCap / kSsBlock;  // consecutive positions per thread in the scan
+static_assert(kSsScanPer == 8, "the mark scan moves 8 u16 marks per thread as one 16-byte word");
 
-// first segment r with ptr[r] >= t*kSsTile, for every window t (tile_seg[ntiles] = n_seg)
+// Per window t: the first segment r with ptr[r] >= t*kSsTile, its start ptr[r], and the start
+// of the segment before it (= the last segment that starts inside window t-1), so that a CTA
+// learns everything about its window from two adjacent 32-byte records (one dependent load).
+struct SsTileRec {
+  int64_t seg;
+  int64_t first;
+  int64_t prev_start;
+  int64_t pad;
+};
+
 template <typename N>
 __global__ void ss_tile_bounds_kernel(const N *__restrict__ ptr, int64_t n_seg, int64_t ntiles,
-                                      int64_t *__restrict__ tile_seg) {
+                                      SsTileRec *__restrict__ rec) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t > ntiles) return;
-  if (t == ntiles) {
-    tile_seg[t] = n_seg;
-    return;
+  int64_t lo = n_seg;
+  if (t < ntiles) {
+    const int64_t target = t * kSsTile;
+    int64_t hi = n_seg;  // lower_bound over ptr[0..n_seg)
+    lo = 0;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)ptr[mid] < target)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
   }
-  const int64_t target = t * kSsTile;
-  int64_t lo = 0, hi = n_seg;  // lower_bound over ptr[0..n_seg)
-  while (lo < hi) {
-    int64_t mid = (lo + hi) >> 1;
-    if ((int64_t)ptr[mid] < target)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
-  tile_seg[t] = lo;
+  SsTileRec r;
+  r.seg = lo;
+  r.first = (int64_t)ptr[lo];
+  r.prev_start = lo > 0 ? (int64_t)ptr[lo - 1] : 0;
+  r.pad = 0;
+  rec[t] = r;
 }
 
-template <typename I, typename V>
+template <typename I, typename N, typename V>
 struct SsSmem {
   I key[kSsCap];
   typename std::conditional<has_val<V>, V, char>::type val[has_val<V> ? kSsCap : 1];
-  unsigned lrow[kSsCap];          // segment number (relative to the window's first) per entry
-  unsigned short sbeg[kSsCap];    // local start / end of the entry's segment
-  unsigned short send[kSsCap];
-  unsigned mid[kSsMaxMid];        // segments of 33..kSsLong entries (relative numbers)
-  unsigned scratch[34];
+  // mark[q]: during the row pass, (q + 1) at the first position of every non-empty segment and
+  // 0 elsewhere; after the scan, (start of q's segment + 1) at every position
+  __align__(16) unsigned short mark[kSsCap];
+  unsigned short len[kSsCap];  // at a segment's first position: its length
+  N base[kSsCap];              // at a segment's first position: source offset of its entries
+  unsigned mid[kSsMaxMid];     // first positions of the segments with 33..kSsLong entries
+  unsigned scratch[kSsBlock / 32];
   unsigned nmid;
 };
 
@@ -72,109 +90,114 @@ __device__ __forceinline__ bool ss_less(I ka, V va, I kb, V vb) {
     return false;
 }
 
-// Loader concept:  int64_t seg_base(int64_t seg)  -- source offset of the segment's first entry
-//                  I key(int64_t src_pos), V val(int64_t src_pos)
+// Loader concept:  int64_t seg_base(int64_t seg)  source offset of the segment's first entry
+//                  I raw_key(int64_t src_pos)      the stored index
+//                  I map_key(I raw)                renumbering applied to it (identity if none)
+//                  V val(int64_t src_pos)
+//
+// Dependent global loads per CTA: window record -> {ptr[r], seg_base(r)} -> raw_key/val ->
+// map_key.  Everything else (which segment a position belongs to, where its source is) is
+// resolved in shared memory: segments mark their first position, an inclusive max-scan spreads
+// the mark, and the per-segment source offset / length sit in tables indexed by that position.
 template <typename I, typename N, typename V, typename Loader>
 __global__ void __launch_bounds__(kSsBlock)
-    ss_tile_kernel(Loader ld, const N *__restrict__ ptr, const int64_t *__restrict__ tile_seg,
+    ss_tile_kernel(Loader ld, const N *__restrict__ ptr, const SsTileRec *__restrict__ rec,
                    I *__restrict__ out_idx, V *__restrict__ out_val,
                    int64_t *__restrict__ long_list, unsigned *__restrict__ long_count) {
   extern __shared__ __align__(16) unsigned char ss_smem_raw[];
-  SsSmem<I, V> &s = *reinterpret_cast<SsSmem<I, V> *>(ss_smem_raw);
+  SsSmem<I, N, V> &s = *reinterpret_cast<SsSmem<I, N, V> *>(ss_smem_raw);
   const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
   const int64_t t = blockIdx.x;
-  const int64_t r0 = tile_seg[t];
-  int64_t r1 = tile_seg[t + 1];
+  const SsTileRec a = rec[t], b = rec[t + 1];
+  // zero the marks while the records are in flight
+  {
+    uint4 *m4 = reinterpret_cast<uint4 *>(s.mark);
+    m4[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x == 0) s.nmid = 0;
+  }
+  const int64_t r0 = a.seg;
+  int64_t r1 = b.seg;
   if (r0 >= r1) return;
+  const int64_t first = a.first;
+  int64_t last = b.first;
   // at most the LAST segment starting in this window can be long (kSsLong >= kSsTile)
-  {
-    const int64_t last_len = (int64_t)ptr[r1] - (int64_t)ptr[r1 - 1];
-    if (last_len > kSsLong) {
-      if (threadIdx.x == 0) long_list[atomicAdd(long_count, 1u)] = r1 - 1;
-      r1--;
-    }
+  if (last - b.prev_start > kSsLong) {
+    if (threadIdx.x == 0) long_list[atomicAdd(long_count, 1u)] = r1 - 1;
+    r1--;
+    last = b.prev_start;
   }
-  if (r0 >= r1) return;
-  const int64_t first = ptr[r0];
-  const int count = (int)((int64_t)ptr[r1] - first);
-  if (count == 0) return;
-
-  if (threadIdx.x == 0) s.nmid = 0;
-  for (int q = threadIdx.x; q < count; q += kSsBlock) s.lrow[q] = 0;
+  const int count = (int)(last - first);
+  if (count <= 0) return;
   __syncthreads();
 
-  // ---- every non-empty segment marks its first position with (relative number + 1) ----
+  // ---- row pass: every non-empty segment records itself at its first position ----
   for (int64_t r = r0 + threadIdx.x; r < r1; r += kSsBlock) {
-    const int64_t sb = (int64_t)ptr[r] - first, se = (int64_t)ptr[r + 1] - first;
+    const int sb = (int)((int64_t)ptr[r] - first), se = (int)((int64_t)ptr[r + 1] - first);
     if (se > sb) {
-      s.lrow[sb] = (unsigned)(r - r0) + 1u;
-      if (se - sb > kSsEnum) s.mid[atomicAdd(&s.nmid, 1u)] = (unsigned)(r - r0);
+      s.mark[sb] = (unsigned short)(sb + 1);
+      s.len[sb] = (unsigned short)(se - sb);
+      s.base[sb] = (N)ld.seg_base(r);
+      if (se - sb > kSsEnum) s.mid[atomicAdd(&s.nmid, 1u)] = (unsigned)sb;
     }
   }
   __syncthreads();
 
-  // ---- propagate segment numbers to every position: inclusive max-scan of the marks ----
+  // ---- inclusive max-scan of the marks: every position learns its segment's start ----
   {
-    constexpr int kPer = kSsCap / kSsBlock;  // consecutive positions per thread
-    const int q0 = threadIdx.x * kPer;
+    uint4 *m4 = reinterpret_cast<uint4 *>(s.mark);
+    uint4 w = m4[threadIdx.x];
+    unsigned h[8] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16,
+                     w.z & 0xffffu, w.z >> 16, w.w & 0xffffu, w.w >> 16};
     unsigned m = 0;
 #pragma unroll
-    for (int k = 0; k < kPer; k++) {
-      int q = q0 + k;
-      unsigned h = q < count ? s.lrow[q] : 0u;
-      m = h > m ? h : m;
-    }
+    for (int k = 0; k < 8; k++) m = h[k] > m ? h[k] : m;
     unsigned inc = m;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      unsigned tt = __shfl_up_sync(0xffffffffu, inc, o);
+      const unsigned tt = __shfl_up_sync(0xffffffffu, inc, o);
       if ((int)lane >= o) inc = tt > inc ? tt : inc;
     }
     if (lane == 31) s.scratch[wid] = inc;
     __syncthreads();
-    unsigned carry = 0;
-    for (unsigned w = 0; w < wid; w++) carry = s.scratch[w] > carry ? s.scratch[w] : carry;
-    unsigned prev = __shfl_up_sync(0xffffffffu, inc, 1);
-    if (lane == 0) prev = 0;
-    unsigned run = prev > carry ? prev : carry;
+    unsigned run = 0;
+    for (unsigned w2 = 0; w2 < wid; w2++) run = s.scratch[w2] > run ? s.scratch[w2] : run;
+    const unsigned prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane > 0) run = prev > run ? prev : run;
 #pragma unroll
-    for (int k = 0; k < kPer; k++) {
-      int q = q0 + k;
-      if (q < count) {
-        unsigned h = s.lrow[q];
-        run = h > run ? h : run;
-        s.lrow[q] = run - 1u;
-      }
+    for (int k = 0; k < 8; k++) {
+      run = h[k] > run ? h[k] : run;
+      h[k] = run;
     }
+    w.x = h[0] | (h[1] << 16);
+    w.y = h[2] | (h[3] << 16);
+    w.z = h[4] | (h[5] << 16);
+    w.w = h[6] | (h[7] << 16);
+    m4[threadIdx.x] = w;
   }
   __syncthreads();
 
-  // ---- gather the entries through the loader (coalesced in the output layout); loads are
-  //      batched 8 deep per thread so that the dependent gathers overlap ----
-  for (int qb = 0; qb < count; qb += kSsBlock * 8) {
-    I k[8];
-    [[maybe_unused]] typename std::conditional<has_val<V>, V, char>::type v[8];
-    int sb[8], se[8];
+  // ---- gather through the loader, coalesced in the output layout; the loads of a batch are
+  //      issued together so that the dependent map_key gathers overlap ----
+  constexpr int kBatch = 4;
+  for (int qb = 0; qb < count; qb += kSsBlock * kBatch) {
+    I raw[kBatch];
+    [[maybe_unused]] typename std::conditional<has_val<V>, V, char>::type v[kBatch];
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
+    for (int u = 0; u < kBatch; u++) {
       const int q = qb + u * kSsBlock + (int)threadIdx.x;
       if (q < count) {
-        const int64_t r = r0 + s.lrow[q];
-        sb[u] = (int)((int64_t)ptr[r] - first);
-        se[u] = (int)((int64_t)ptr[r + 1] - first);
-        const int64_t p = ld.seg_base(r) + (q - sb[u]);
-        k[u] = ld.key(p);
+        const int sb = (int)s.mark[q] - 1;
+        const int64_t p = (int64_t)s.base[sb] + (q - sb);
+        raw[u] = ld.raw_key(p);
         if constexpr (has_val<V>) v[u] = ld.val(p);
       }
     }
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
+    for (int u = 0; u < kBatch; u++) {
       const int q = qb + u * kSsBlock + (int)threadIdx.x;
       if (q < count) {
-        s.key[q] = k[u];
+        s.key[q] = ld.map_key(raw[u]);
         if constexpr (has_val<V>) s.val[q] = v[u];
-        s.sbeg[q] = (unsigned short)sb[u];
-        s.send[q] = (unsigned short)se[u];
       }
     }
   }
@@ -182,11 +205,12 @@ __global__ void __launch_bounds__(kSsBlock)
 
   // ---- short segments: rank by enumeration, write straight to the final position ----
   for (int q = threadIdx.x; q < count; q += kSsBlock) {
-    const int sb = s.sbeg[q], se = s.send[q];
-    if (se - sb > kSsEnum) continue;
+    const int sb = (int)s.mark[q] - 1;
+    const int len = s.len[sb];
+    if (len > kSsEnum) continue;
     const I k = s.key[q];
     int rank = 0;
-    for (int j = sb; j < se; j++) {
+    for (int j = sb; j < sb + len; j++) {
       const I kj = s.key[j];
       rank += (kj < k || (kj == k && j < q)) ? 1 : 0;
     }
@@ -197,8 +221,7 @@ __global__ void __launch_bounds__(kSsBlock)
   // ---- mid segments: one warp each, normalized bitonic network in shared memory ----
   const unsigned nmid = s.nmid;
   for (unsigned mi = wid; mi < nmid; mi += kSsBlock / 32) {
-    const int64_t r = r0 + s.mid[mi];
-    const int sb = (int)((int64_t)ptr[r] - first), len = (int)((int64_t)ptr[r + 1] - ptr[r]);
+    const int sb = (int)s.mid[mi], len = s.len[sb];
     I *key = s.key + sb;
     int P = 64;
     while (P < len) P <<= 1;
@@ -207,23 +230,23 @@ __global__ void __launch_bounds__(kSsBlock)
         const bool flip = (j == (k >> 1));
         for (int x = lane; x < (P >> 1); x += 32) {
           // x-th comparator of this step: low index a has bit j clear
-          const int a = ((x & ~(j - 1)) << 1) | (x & (j - 1));
-          const int b = flip ? (a ^ (k - 1)) : (a | j);
-          if (b < len) {
-            const I ka = key[a], kb = key[b];
+          const int a2 = ((x & ~(j - 1)) << 1) | (x & (j - 1));
+          const int b2 = flip ? (a2 ^ (k - 1)) : (a2 | j);
+          if (b2 < len) {
+            const I ka = key[a2], kb = key[b2];
             if constexpr (has_val<V>) {
               V *val = reinterpret_cast<V *>(s.val) + sb;
-              const V va = val[a], vb = val[b];
+              const V va = val[a2], vb = val[b2];
               if (ss_less<I, V>(kb, vb, ka, va)) {
-                key[a] = kb;
-                key[b] = ka;
-                val[a] = vb;
-                val[b] = va;
+                key[a2] = kb;
+                key[b2] = ka;
+                val[a2] = vb;
+                val[b2] = va;
               }
             } else {
               if (kb < ka) {
-                key[a] = kb;
-                key[b] = ka;
+                key[a2] = kb;
+                key[b2] = ka;
               }
             }
           }
@@ -267,7 +290,7 @@ __global__ void ss_long_fill_kernel(Loader ld, const N *__restrict__ ptr,
     }
     const int64_t r = list[lo];
     const int64_t p = ld.seg_base(r) + (e - offs[lo]);
-    keys[e] = ((uint64_t)lo << idx_bits) | (uint64_t)ld.key(p);
+    keys[e] = ((uint64_t)lo << idx_bits) | (uint64_t)ld.map_key(ld.raw_key(p));
     if constexpr (has_val<V>) vals[e] = ld.val(p);
   }
 }
@@ -298,18 +321,18 @@ void segmented_sort(Workspace &ws, Loader ld, const N *ptr, int64_t n_seg, int64
   if (nnz <= 0 || n_seg <= 0) return;
   cudaStream_t st = ws.stream();
   const int64_t ntiles = ceil_div(nnz, kSsTile);
-  int64_t *tile_seg = ws.alloc<int64_t>(ntiles + 1);
+  SsTileRec *tile_rec = ws.alloc<SsTileRec>(ntiles + 1);
   // every long segment is the last one of a distinct window
   int64_t *long_list = ws.alloc<int64_t>(ntiles + 1);
   unsigned *long_count = ws.alloc<unsigned>(1);
   SB_CUDA(cudaMemsetAsync(long_count, 0, sizeof(unsigned), st));
   SB_LAUNCH((ss_tile_bounds_kernel<N>), (unsigned)ceil_div(ntiles + 1, 256), 256, 0, st, ptr,
-            n_seg, ntiles, tile_seg);
+            n_seg, ntiles, tile_rec);
   auto kern = ss_tile_kernel<I, N, V, Loader>;
   SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)sizeof(SsSmem<I, V>)));
-  SB_LAUNCH(kern, (unsigned)ntiles, kSsBlock, sizeof(SsSmem<I, V>), st, ld, ptr, tile_seg,
-            out_idx, out_val, long_list, long_count);
+                               (int)sizeof(SsSmem<I, N, V>)));
+  SB_LAUNCH(kern, (unsigned)ntiles, kSsBlock, sizeof(SsSmem<I, N, V>), st, ld, ptr,
+            (const SsTileRec *)tile_rec, out_idx, out_val, long_list, long_count);
   unsigned nlong = 0;
   SB_CUDA(cudaMemcpyAsync(&nlong, long_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));

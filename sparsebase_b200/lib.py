@@ -188,7 +188,8 @@ def rcm_last_stats():
     d = dict(zip(("levels_narrow", "levels_wide", "bfs", "components"), list(out)))
     cyc = (ctypes.c_int64 * 8)()
     _check(load().sb200_rcm_last_cycles(cyc))
-    d["phase_cycles"] = dict(zip(("load", "claim", "check", "finalize", "write"), list(cyc)[:5]))
+    d["phase_cycles"] = dict(zip(("seek", "claim", "barrier1", "recheck", "compact", "exchange",
+                                  "sort_write", "rescan"), list(cyc)))
     return d
 
 

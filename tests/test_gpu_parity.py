@@ -376,3 +376,37 @@ def test_no_cpu_fallback_error_path(sb):
     rc = lib.sb200_degrees(0, ctypes.c_int64(4), ctypes.c_void_p(8), ctypes.c_void_p(8),
                            sb.F32, sb.I32, None)
     assert rc == 2 and b"id_type" in lib.sb200_last_error()
+
+
+@pytest.mark.parametrize("shape", [(1500, 1111), (64, 20000), (3000, 7)])
+def test_rcm_wide_grids_cluster_regime(sb, orc, shape):
+    """Frontiers of hundreds to thousands of vertices: the cluster kernel keeps every CTA's
+    share resident across levels and re-splits when the shares drift (rcm.cu cl_reload)."""
+    n, rp, col, _ = graphs.poisson(*shape)
+    exp = orc.rcm_reorder(n, rp, col)
+    got = host(sb.rcm_reorder(n, dev(rp), dev(col)))
+    assert eq(got, exp), f"rcm mismatch at {np.flatnonzero(got != exp)[:10]}"
+    st = sb.rcm_last_stats()
+    assert st["levels_narrow"] > 0 and st["levels_wide"] == 0
+
+
+def test_permute2d_short_rows_kernel(sb, orc):
+    """Matrices whose longest row has <= 8 entries take the warp-transposed register-sort
+    kernel (reorder.cu permute_short_rows_kernel); empty rows, every type combination."""
+    rng = np.random.default_rng(77)
+    n = 50021
+    deg = rng.integers(0, 9, size=n)
+    deg[rng.integers(0, n, size=500)] = 0
+    row = np.repeat(np.arange(n), deg)
+    col = np.concatenate([rng.choice(n, size=d, replace=False) for d in deg]).astype(np.int64)
+    for idt, nt, vt in TYPES:
+        rp = graphs.csr_of(n, row.astype(idt), col.astype(idt), nt)
+        cc = col.astype(idt)
+        vv = None if vt is None else graphs.vals_for(len(cc), dtype=vt)
+        # CSR rows must be sorted for the oracle's input contract
+        cc2, vv2 = orc.csr_ctor_sort(n, n, rp, cc, vv)
+        order = rng.permutation(n).astype(idt)
+        exp = orc.permute2d(n, n, rp, cc2, vv2, order, order)
+        got = sb.permute2d(n, n, dev(rp), dev(cc2), dev(vv2), dev(order), dev(order))
+        for a, b, what in zip(got, exp, ("row_ptr", "col", "vals")):
+            assert eq(host(a), b), f"short-row permute2d {what} {idt} {nt} {vt}"
