@@ -147,6 +147,11 @@ int sb200_rcm_reorder(int device, int64_t n, int64_t nnz, const void *row_ptr, c
  * h_out4 = {levels walked by the persistent single-CTA kernel, levels done with grid-wide
  * kernels, number of BFS traversals, number of non-trivial connected components}. */
 int sb200_rcm_last_stats(int64_t *h_out4);
+/* The BFS traversals of peripheral() after the first are run as the Cuthill-McKee traversal
+ * itself (same level sets).  h_out3 = {confirmed: eccentricity did not grow, one BFS saved;
+ * continued: it grew and the new root was unique by degree, no replay needed; replayed: it grew
+ * and the new root depended on the FIFO order, the BFS was repeated literally}. */
+int sb200_rcm_last_speculation(int64_t *h_out3);
 /* SM-cycle counters of the narrow regime's per-level phases {seek, claim, barrier 1, recheck,
  * compaction, count exchange (barrier 2), sibling sort + queue write, degree rescan}
  * accumulated by CTA 0 (profiling aid). */

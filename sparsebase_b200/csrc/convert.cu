@@ -33,8 +33,9 @@ __global__ void __launch_bounds__(kBfBlock)
     boundary_fill_copy_kernel(const I *__restrict__ idx, const I *__restrict__ sec,
                               const V *__restrict__ vals, int64_t nnz, int64_t n_seg,
                               I idx_base, N *__restrict__ ptr, I *__restrict__ out_sec,
-                              V *__restrict__ out_vals, unsigned *__restrict__ flags) {
-  const int64_t base = ((int64_t)blockIdx.x * kBfBlock) * kBfIpt;
+                              V *__restrict__ out_vals, unsigned *__restrict__ flags,
+                              int64_t start) {
+  const int64_t base = start + ((int64_t)blockIdx.x * kBfBlock) * kBfIpt;
   bool inv = false, sec_unsorted = false;
   I my[kBfIpt], prev[kBfIpt], ms[kBfIpt], ps[kBfIpt];
 #pragma unroll
@@ -71,6 +72,98 @@ __global__ void __launch_bounds__(kBfBlock)
       for (int64_t r = lo; r <= hi; r++) ptr[r] = (N)i;
       if (i == nnz - 1)
         for (int64_t r = (int64_t)my[k] + 1; r <= n_seg; r++) ptr[r] = (N)nnz;
+    }
+  }
+  if (__any_sync(0xffffffffu, inv) && lane_id() == 0) atomicOr(&flags[0], 1u);
+  if (__any_sync(0xffffffffu, sec_unsorted) && lane_id() == 0) atomicOr(&flags[1], 1u);
+}
+
+// ---- 128-bit variant: every thread owns kBvLoads * (16 / sizeof(I)) CONSECUTIVE elements and
+//      moves them with 16-byte loads and stores, all loads of the thread issued before the first
+//      use (48-96 bytes in flight per thread).  The element before a thread's first one comes
+//      from the neighbouring lane by shuffle (lane 0 reads it from L2).  Needs 16-byte aligned
+//      arrays; handles the first (nnz / E) * E elements, the scalar kernel finishes the tail. ----
+constexpr int kBvBlock = 256;
+constexpr int kBvLoads = 2;
+
+template <typename I, typename N, typename V>
+__global__ void __launch_bounds__(kBvBlock)
+    boundary_fill_copy_vec_kernel(const I *__restrict__ idx, const I *__restrict__ sec,
+                                  const V *__restrict__ vals, int64_t nnz, int64_t ngroups,
+                                  int64_t n_seg, I idx_base, N *__restrict__ ptr,
+                                  I *__restrict__ out_sec, V *__restrict__ out_vals,
+                                  unsigned *__restrict__ flags) {
+  constexpr int kPer = 16 / sizeof(I);      // elements per 16-byte word
+  constexpr int E = kBvLoads * kPer;        // elements per thread
+  using VR = typename std::conditional<has_val<V>, V, I>::type;
+  constexpr int kVw = has_val<V> ? (E * (int)sizeof(VR)) / 16 : 1;  // 16-byte words of values
+  const int64_t g = (int64_t)blockIdx.x * kBvBlock + threadIdx.x;
+  const bool active = g < ngroups;
+  const int64_t i0 = g * E;
+  union W {
+    uint4 q;
+    I e[kPer];
+  };
+  W a[kBvLoads], b[kBvLoads];
+  uint4 v[kVw];
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < kBvLoads; k++) a[k].q = __ldcs(reinterpret_cast<const uint4 *>(idx + i0) + k);
+    if (sec) {
+#pragma unroll
+      for (int k = 0; k < kBvLoads; k++)
+        b[k].q = __ldcs(reinterpret_cast<const uint4 *>(sec + i0) + k);
+    }
+    if constexpr (has_val<V>) {
+      if (out_vals) {
+#pragma unroll
+        for (int k = 0; k < kVw; k++) v[k] = __ldcs(reinterpret_cast<const uint4 *>(vals + i0) + k);
+      }
+    }
+  }
+  // the element before this thread's first one
+  I last_idx = active ? a[kBvLoads - 1].e[kPer - 1] : I(0);
+  I last_sec = (active && sec) ? b[kBvLoads - 1].e[kPer - 1] : I(0);
+  I prev_idx = __shfl_up_sync(0xffffffffu, last_idx, 1);
+  I prev_sec = __shfl_up_sync(0xffffffffu, last_sec, 1);
+  if (active && lane_id() == 0) {
+    prev_idx = i0 > 0 ? idx[i0 - 1] : idx_base;  // (0 after the base is subtracted)
+    prev_sec = (i0 > 0 && sec) ? sec[i0 - 1] : I(0);
+  }
+  bool inv = false, sec_unsorted = false;
+  if (active) {
+    if (sec && out_sec) {
+#pragma unroll
+      for (int k = 0; k < kBvLoads; k++) __stcs(reinterpret_cast<uint4 *>(out_sec + i0) + k, b[k].q);
+    }
+    if constexpr (has_val<V>) {
+      if (out_vals) {
+#pragma unroll
+        for (int k = 0; k < kVw; k++) __stcs(reinterpret_cast<uint4 *>(out_vals + i0) + k, v[k]);
+      }
+    }
+    I p = prev_idx - idx_base, ps = prev_sec;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const int64_t i = i0 + k;
+      const I my = a[k / kPer].e[k % kPer] - idx_base;
+      if (my < p) inv = true;
+      if (sec) {
+        const I ms = b[k / kPer].e[k % kPer];
+        if (i > 0 && my == p && ms < ps) sec_unsorted = true;
+        if (ms < 0) sec_unsorted = true;
+        ps = ms;
+      }
+      if (my != p || i == 0) {
+        int64_t lo = i > 0 ? (int64_t)p + 1 : 0;
+        int64_t hi = (int64_t)my;
+        if (hi >= n_seg) hi = n_seg - 1;
+        if (lo < 0) lo = 0;
+        for (int64_t r = lo; r <= hi; r++) ptr[r] = (N)i;
+      }
+      if (i == nnz - 1)
+        for (int64_t r = (int64_t)my + 1; r <= n_seg; r++) ptr[r] = (N)nnz;
+      p = my;
     }
   }
   if (__any_sync(0xffffffffu, inv) && lane_id() == 0) atomicOr(&flags[0], 1u);
@@ -121,9 +214,24 @@ void build_ptr_and_copy(Workspace &ws, const I *idx, const I *sec, const V *vals
     h_flags[0] = h_flags[1] = 0;
     return;
   }
-  const int64_t per_block = (int64_t)kBfBlock * kBfIpt;
-  SB_LAUNCH((boundary_fill_copy_kernel<I, N, V>), (unsigned)ceil_div(nnz, per_block), kBfBlock,
-            0, st, idx, sec, vals, nnz, n_seg, idx_base, ptr, out_sec, out_vals, flags);
+  // 16-byte path for the bulk, scalar path for the tail (or everything if unaligned)
+  constexpr int kE = kBvLoads * (16 / (int)sizeof(I));
+  auto aligned16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  int64_t done = 0;
+  if (aligned16(idx) && aligned16(sec) && aligned16(vals) && aligned16(out_sec) &&
+      aligned16(out_vals) && nnz >= kE) {
+    const int64_t ngroups = nnz / kE;
+    SB_LAUNCH((boundary_fill_copy_vec_kernel<I, N, V>), (unsigned)ceil_div(ngroups, kBvBlock),
+              kBvBlock, 0, st, idx, sec, vals, nnz, ngroups, n_seg, idx_base, ptr, out_sec,
+              out_vals, flags);
+    done = ngroups * kE;
+  }
+  if (done < nnz) {
+    const int64_t per_block = (int64_t)kBfBlock * kBfIpt;
+    SB_LAUNCH((boundary_fill_copy_kernel<I, N, V>), (unsigned)ceil_div(nnz - done, per_block),
+              kBfBlock, 0, st, idx, sec, vals, nnz, n_seg, idx_base, ptr, out_sec, out_vals, flags,
+              done);
+  }
   SB_CUDA(cudaMemcpyAsync(h_flags, flags, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   if (h_flags[0]) {

@@ -24,10 +24,9 @@
 
 namespace sb200 {
 
+// upsweep block (the downsweep block / tile are template parameters, see rs_config)
 constexpr int kRsBlock = 256;
 constexpr int kRsWarps = kRsBlock / 32;
-constexpr int kRsIpt = 12;
-constexpr int kRsTile = kRsBlock * kRsIpt;  // 3072 records per tile
 constexpr int kRsMaxBits = 8;
 constexpr int kRsMaxBins = 1 << kRsMaxBits;
 
@@ -38,8 +37,9 @@ __device__ __forceinline__ unsigned rs_digit(K key, int shift, unsigned mask) {
 
 struct RsChunking {
   int64_t n;
-  int64_t tiles;
+  int64_t tiles;  // in units of `tile` records (the downsweep tile of the chosen configuration)
   int nchunks;
+  int tile;
   __host__ __device__ int64_t tile_begin(int c) const { return tiles * c / nchunks; }
   __host__ __device__ int64_t tile_end(int c) const { return tiles * (c + 1) / nchunks; }
 };
@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(kRsBlock)
   for (int i = threadIdx.x; i < kRsWarps * kRsMaxBins; i += kRsBlock) (&hist[0][0])[i] = 0;
   __syncthreads();
   const int c = blockIdx.x;
-  const int64_t begin = ch.tile_begin(c) * kRsTile;
-  int64_t end = ch.tile_end(c) * kRsTile;
+  const int64_t begin = ch.tile_begin(c) * ch.tile;
+  int64_t end = ch.tile_end(c) * ch.tile;
   if (end > ch.n) end = ch.n;
   const bool aligned = (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
   int64_t base = begin;
@@ -104,55 +104,40 @@ __global__ void __launch_bounds__(kRsBlock)
 }
 
 // ------------------------------------------------------------------ downsweep
+// Per tile of BLOCK * IPT records:
+//   1. stable rank of every record among the records of its digit inside its warp
+//      (match_any: rounds in order, lanes in order) with warp-private digit counters
+//   2. per digit: exclusive scan over the warps, then over the digits (tile histogram);
+//      delta[d] = (running global offset of digit d for this chunk) - (first slot of d in the tile)
+//   3. key AND payloads are staged in shared memory at their tile-local sorted slot
+//   4. slot j goes to global position delta[digit(key_j)] + j: consecutive slots of one digit
+//      are consecutive in global memory, so every warp store is a few contiguous runs, and the
+//      destination is computed once for the three arrays
+// Nothing of a tile is re-read from global memory; the keys of the next tile are requested
+// before the current one is ranked.  Off = int32 when n < 2^31 halves the shared-memory traffic
+// of step 4.
+template <int BLOCK, int IPT, typename K, typename V1, typename V2, typename Off>
 struct RsSmem {
-  unsigned cnt[kRsWarps][kRsMaxBins];
+  static constexpr int kTile = BLOCK * IPT;
+  unsigned cnt[BLOCK / 32][kRsMaxBins];
   int64_t bin_off[kRsMaxBins];
-  int64_t delta[kRsMaxBins];
-  unsigned tile_base[kRsMaxBins];
+  Off delta[kRsMaxBins];
   unsigned scan_scratch[34];
-  unsigned char sdig[kRsTile];
-  uint64_t stage[kRsTile];
+  K sk[kTile];
+  typename std::conditional<has_val<V1>, V1, char>::type s1[has_val<V1> ? kTile : 1];
+  typename std::conditional<has_val<V2>, V2, char>::type s2[has_val<V2> ? kTile : 1];
 };
 
-template <typename T>
-__device__ __forceinline__ void rs_load_payload(const T *__restrict__ in, int64_t warp_base,
-                                                int64_t n, T (&v)[kRsIpt]) {
-  const unsigned lane = lane_id();
-#pragma unroll
-  for (int r = 0; r < kRsIpt; r++) {
-    int64_t i = warp_base + r * 32 + lane;
-    if (i < n) v[r] = ld_stream(in + i);
-  }
-}
-
-template <typename T>
-__device__ __forceinline__ void rs_store_payload(const T (&v)[kRsIpt], T *__restrict__ out,
-                                                 RsSmem &s, int64_t warp_base, int64_t n,
-                                                 const unsigned (&lp)[kRsIpt], int tile_count) {
-  T *stage = reinterpret_cast<T *>(s.stage);
-  const unsigned lane = lane_id();
-#pragma unroll
-  for (int r = 0; r < kRsIpt; r++) {
-    int64_t i = warp_base + r * 32 + lane;
-    if (i < n) stage[lp[r]] = v[r];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < kRsIpt; k++) {
-    int j = k * kRsBlock + threadIdx.x;
-    if (j < tile_count) out[s.delta[s.sdig[j]] + j] = stage[j];
-  }
-  __syncthreads();
-}
-
-template <typename K, typename V1, typename V2>
-__global__ void __launch_bounds__(kRsBlock, 2)
+template <int BLOCK, int IPT, int MINB, typename K, typename V1, typename V2, typename Off>
+__global__ void __launch_bounds__(BLOCK, MINB)
     rs_downsweep_kernel(const K *__restrict__ kin, K *__restrict__ kout,
                         const V1 *__restrict__ v1in, V1 *__restrict__ v1out,
                         const V2 *__restrict__ v2in, V2 *__restrict__ v2out, RsChunking ch,
                         int shift, int bits, const int64_t *__restrict__ spine) {
+  using Smem = RsSmem<BLOCK, IPT, K, V1, V2, Off>;
+  constexpr int kTile = BLOCK * IPT;
   extern __shared__ __align__(16) unsigned char rs_smem_raw[];
-  RsSmem &s = *reinterpret_cast<RsSmem *>(rs_smem_raw);
+  Smem &s = *reinterpret_cast<Smem *>(rs_smem_raw);
   const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
   const unsigned mask = (1u << bits) - 1u;
   const int nbins = 1 << bits;
@@ -162,46 +147,54 @@ __global__ void __launch_bounds__(kRsBlock, 2)
   if ((int)threadIdx.x < nbins)
     s.bin_off[threadIdx.x] = spine[(int64_t)threadIdx.x * ch.nchunks + c];
 
-  // software pipeline: the keys of tile t+1 are requested before tile t is processed, so the
-  // ranking of a tile never waits for its own loads (ncu: 37% of the stall samples sat on the
-  // first use of the freshly loaded keys before this)
-  K key[kRsIpt], nkey[kRsIpt];
+  K key[IPT], nkey[IPT];
   {
-    const int64_t wb = ch.tile_begin(c) * kRsTile + (int64_t)wid * (kRsIpt * 32);
+    const int64_t wb = ch.tile_begin(c) * kTile + (int64_t)wid * (IPT * 32);
 #pragma unroll
-    for (int r = 0; r < kRsIpt; r++) {
-      int64_t i = wb + r * 32 + lane;
+    for (int r = 0; r < IPT; r++) {
+      const int64_t i = wb + r * 32 + lane;
       nkey[r] = i < n ? ld_stream(kin + i) : K(0);
     }
   }
   for (int64_t tile = ch.tile_begin(c); tile < ch.tile_end(c); tile++) {
-    const int64_t tile_base_idx = tile * kRsTile;
+    const int64_t tile_base_idx = tile * kTile;
     const int64_t rem = n - tile_base_idx;
-    const int tile_count = rem < kRsTile ? (int)rem : kRsTile;
-    const int64_t warp_base = tile_base_idx + (int64_t)wid * (kRsIpt * 32);
+    const int tile_count = rem < kTile ? (int)rem : kTile;
+    const int64_t warp_base = tile_base_idx + (int64_t)wid * (IPT * 32);
 
-    for (int i = threadIdx.x; i < kRsWarps * kRsMaxBins; i += kRsBlock) (&s.cnt[0][0])[i] = 0;
-
+    for (int i = threadIdx.x; i < (BLOCK / 32) * kRsMaxBins; i += BLOCK) (&s.cnt[0][0])[i] = 0;
 #pragma unroll
-    for (int r = 0; r < kRsIpt; r++) key[r] = nkey[r];
+    for (int r = 0; r < IPT; r++) key[r] = nkey[r];
     if (tile + 1 < ch.tile_end(c)) {
 #pragma unroll
-      for (int r = 0; r < kRsIpt; r++) {
-        int64_t i = warp_base + kRsTile + r * 32 + lane;
+      for (int r = 0; r < IPT; r++) {
+        const int64_t i = warp_base + kTile + r * 32 + lane;
         nkey[r] = i < n ? ld_stream(kin + i) : K(0);
       }
     }
     // payload loads of this tile are issued now and consumed after the ranking
-    [[maybe_unused]] typename std::conditional<has_val<V1>, V1, char>::type p1[kRsIpt];
-    [[maybe_unused]] typename std::conditional<has_val<V2>, V2, char>::type p2[kRsIpt];
-    if constexpr (has_val<V1>) rs_load_payload<V1>(v1in, warp_base, n, p1);
-    if constexpr (has_val<V2>) rs_load_payload<V2>(v2in, warp_base, n, p2);
-    __syncthreads();  // counters zeroed
-
-    // ---- stable ranking inside the warp: rounds in order, lanes in order ----
-    unsigned lp[kRsIpt];
+    [[maybe_unused]] typename std::conditional<has_val<V1>, V1, char>::type p1[IPT];
+    [[maybe_unused]] typename std::conditional<has_val<V2>, V2, char>::type p2[IPT];
+    if constexpr (has_val<V1>) {
 #pragma unroll
-    for (int r = 0; r < kRsIpt; r++) {
+      for (int r = 0; r < IPT; r++) {
+        const int64_t i = warp_base + r * 32 + lane;
+        if (i < n) p1[r] = ld_stream(v1in + i);
+      }
+    }
+    if constexpr (has_val<V2>) {
+#pragma unroll
+      for (int r = 0; r < IPT; r++) {
+        const int64_t i = warp_base + r * 32 + lane;
+        if (i < n) p2[r] = ld_stream(v2in + i);
+      }
+    }
+    __syncthreads();  // counters zeroed; everybody is done with the previous tile's staging
+
+    // ---- 1. stable ranking inside the warp ----
+    unsigned lp[IPT];
+#pragma unroll
+    for (int r = 0; r < IPT; r++) {
       const bool valid = warp_base + r * 32 + lane < n;
       const unsigned d = valid ? rs_digit(key[r], shift, mask) : 0xffffffffu;
       const unsigned peers = __match_any_sync(0xffffffffu, d);
@@ -217,47 +210,55 @@ __global__ void __launch_bounds__(kRsBlock, 2)
     }
     __syncthreads();
 
-    // ---- per digit: exclusive scan over warps, then exclusive scan over digits ----
+    // ---- 2. per digit: exclusive scan over warps, then exclusive scan over digits ----
     unsigned hist = 0;
     if ((int)threadIdx.x < nbins) {
       unsigned run = 0;
 #pragma unroll
-      for (int w = 0; w < kRsWarps; w++) {
-        unsigned t = s.cnt[w][threadIdx.x];
+      for (int w = 0; w < BLOCK / 32; w++) {
+        const unsigned t = s.cnt[w][threadIdx.x];
         s.cnt[w][threadIdx.x] = run;
         run += t;
       }
       hist = run;
     }
-    unsigned excl = block_exclusive_scan(hist, s.scan_scratch);
+    const unsigned excl = block_exclusive_scan(hist, s.scan_scratch);
     if ((int)threadIdx.x < nbins) {
-      s.tile_base[threadIdx.x] = excl;
-      int64_t off = s.bin_off[threadIdx.x];
-      s.delta[threadIdx.x] = off - (int64_t)excl;
+#pragma unroll
+      for (int w = 0; w < BLOCK / 32; w++) s.cnt[w][threadIdx.x] += excl;  // tile-local slot base
+      const int64_t off = s.bin_off[threadIdx.x];
+      s.delta[threadIdx.x] = (Off)(off - (int64_t)excl);
       s.bin_off[threadIdx.x] = off + hist;
     }
     __syncthreads();
 
-    // ---- keys: stage in digit order, then coalesced runs to global ----
-    K *stage_k = reinterpret_cast<K *>(s.stage);
+    // ---- 3. stage the records at their tile-local sorted slot ----
 #pragma unroll
-    for (int r = 0; r < kRsIpt; r++) {
+    for (int r = 0; r < IPT; r++) {
       if (warp_base + r * 32 + lane < n) {
         const unsigned d = rs_digit(key[r], shift, mask);
-        lp[r] += s.tile_base[d] + s.cnt[wid][d];
-        stage_k[lp[r]] = key[r];
-        s.sdig[lp[r]] = (unsigned char)d;
+        const unsigned at = lp[r] + s.cnt[wid][d];
+        s.sk[at] = key[r];
+        if constexpr (has_val<V1>) s.s1[at] = p1[r];
+        if constexpr (has_val<V2>) s.s2[at] = p2[r];
       }
     }
     __syncthreads();
+
+    // ---- 4. coalesced runs to global memory ----
 #pragma unroll
-    for (int k = 0; k < kRsIpt; k++) {
-      int j = k * kRsBlock + threadIdx.x;
-      if (j < tile_count) kout[s.delta[s.sdig[j]] + j] = stage_k[j];
+    for (int k = 0; k < IPT; k++) {
+      const int j = k * BLOCK + (int)threadIdx.x;
+      if (j < tile_count) {
+        const K kk = s.sk[j];
+        const int64_t dst = (int64_t)s.delta[rs_digit(kk, shift, mask)] + j;
+        kout[dst] = kk;
+        if constexpr (has_val<V1>) v1out[dst] = s.s1[j];
+        if constexpr (has_val<V2>) v2out[dst] = s.s2[j];
+      }
     }
-    __syncthreads();
-    if constexpr (has_val<V1>) rs_store_payload<V1>(p1, v1out, s, warp_base, n, lp, tile_count);
-    if constexpr (has_val<V2>) rs_store_payload<V2>(p2, v2out, s, warp_base, n, lp, tile_count);
+    // no barrier here: the next tile writes cnt (last read in step 3), and touches delta and
+    // the staging arrays only after its own first two barriers
   }
 }
 
@@ -295,6 +296,44 @@ struct RsBufs {
   V2 *v2;
 };
 
+// One downsweep launch for a fixed (BLOCK, IPT, MINB) configuration.
+template <int BLOCK, int IPT, int MINB, typename K, typename V1, typename V2>
+void rs_launch_downsweep(cudaStream_t st, RsBufs<K, V1, V2> src, RsBufs<K, V1, V2> dst,
+                         const RsChunking &ch, int shift, int bits, const int64_t *spine) {
+  if (ch.n < (1ll << 31)) {
+    auto kern = rs_downsweep_kernel<BLOCK, IPT, MINB, K, V1, V2, int32_t>;
+    constexpr int smem = (int)sizeof(RsSmem<BLOCK, IPT, K, V1, V2, int32_t>);
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SB_LAUNCH(kern, ch.nchunks, BLOCK, smem, st, (const K *)src.k, dst.k, (const V1 *)src.v1,
+              dst.v1, (const V2 *)src.v2, dst.v2, ch, shift, bits, spine);
+  } else {
+    auto kern = rs_downsweep_kernel<BLOCK, IPT, MINB, K, V1, V2, int64_t>;
+    constexpr int smem = (int)sizeof(RsSmem<BLOCK, IPT, K, V1, V2, int64_t>);
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SB_LAUNCH(kern, ch.nchunks, BLOCK, smem, st, (const K *)src.k, dst.k, (const V1 *)src.v1,
+              dst.v1, (const V2 *)src.v2, dst.v2, ch, shift, bits, spine);
+  }
+}
+
+// Downsweep configuration: 512 threads x 8 records (4096-record tile, two CTAs per SM, 32
+// resident warps).  SB200_RS_CONFIG selects the alternatives kept for tuning runs.
+inline int rs_config() {
+  static const int cfg = [] {
+    const char *e = getenv("SB200_RS_CONFIG");
+    return e ? atoi(e) : 0;
+  }();
+  return cfg;
+}
+inline int rs_config_tile(int cfg) {
+  switch (cfg) {
+    case 1: return 256 * 12;
+    case 2: return 512 * 12;
+    case 3: return 384 * 10;
+    case 4: return 256 * 16;
+    default: return 512 * 8;
+  }
+}
+
 // Stable sort of n records by the given key bit ranges (least significant range first).
 // `in` is only read; the sorted records always land in `out`; `tmp` is scratch of the same
 // size and is only touched when more than one pass is needed (rs_num_passes(ranges) > 1).
@@ -313,16 +352,15 @@ void radix_sort(Workspace &ws, RsBufs<K, V1, V2> in, RsBufs<K, V1, V2> out,
     return;
   }
   const DeviceInfo &di = device_info(ws.device());
+  const int cfg = rs_config();
   RsChunking ch;
   ch.n = n;
-  ch.tiles = ceil_div(n, kRsTile);
+  ch.tile = rs_config_tile(cfg);
+  ch.tiles = ceil_div(n, ch.tile);
   int64_t max_chunks = (int64_t)di.sm_count * 4;
   ch.nchunks = (int)(ch.tiles < max_chunks ? ch.tiles : max_chunks);
   int64_t *spine_in = ws.alloc<int64_t>((int64_t)kRsMaxBins * ch.nchunks + 1);
   int64_t *spine = ws.alloc<int64_t>((int64_t)kRsMaxBins * ch.nchunks + 1);
-  auto kern = rs_downsweep_kernel<K, V1, V2>;
-  SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)sizeof(RsSmem)));
   int pass = 0;
   RsBufs<K, V1, V2> src = in;
   for (const RsBitRange &rg : ranges) {
@@ -337,9 +375,16 @@ void radix_sort(Workspace &ws, RsBufs<K, V1, V2> in, RsBufs<K, V1, V2> out,
                 bits, spine_in);
       exclusive_scan<int64_t>(ws, LoadFn<int64_t>{spine_in}, spine,
                               (int64_t)(1 << bits) * ch.nchunks);
-      SB_LAUNCH(kern, ch.nchunks, kRsBlock, sizeof(RsSmem), st, (const K *)src.k, dst.k,
-                (const V1 *)src.v1, dst.v1, (const V2 *)src.v2, dst.v2, ch, shift, bits,
-                (const int64_t *)spine);
+      if (cfg == 1)
+        rs_launch_downsweep<256, 12, 2, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
+      else if (cfg == 2)
+        rs_launch_downsweep<512, 12, 1, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
+      else if (cfg == 3)
+        rs_launch_downsweep<384, 10, 2, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
+      else if (cfg == 4)
+        rs_launch_downsweep<256, 16, 2, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
+      else
+        rs_launch_downsweep<512, 8, 2, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
       src = dst;
       shift += bits;
     }

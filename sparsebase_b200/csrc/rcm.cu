@@ -58,10 +58,12 @@ struct RcmState {
   int32_t phase;
   int32_t status;
   int32_t next_phase_after_reset;
-  int32_t pad;
+  int32_t spec;  // 1: the running CM BFS stands in for a BFS of peripheral() (PH_PBFS_END)
   int64_t frontier_maxdeg;  // max degree over the current frontier (for the narrow caps)
   int64_t key_base;    // peripheral BFS: expansion slots of all earlier levels (monotone claim keys)
   int64_t inv_qst, inv_end;  // pending bulk inversion
+  int64_t reset_cm;    // pending bulk reset walks Q[qst, lvl_end) instead of Qp[0, lvl_end)
+  int64_t stat_spec_ok, stat_spec_fail, stat_spec_chain;
   int64_t stat_levels_narrow, stat_levels_wide, stat_bfs, stat_components;
   int64_t cyc[8];  // narrow-level phase cycle counters (CTA 0): load, claim, check, finalize, write
 };
@@ -81,6 +83,7 @@ struct RcmArgs {
   I *inv;  // result: inv[Qp2[i]] = i
   RcmState *state;
   int force_wide;  // testing: never take the narrow path
+  int no_spec;     // testing: never run a peripheral BFS speculatively as the CM BFS
 };
 
 // ------------------------------------------------------------------------------------
@@ -519,6 +522,43 @@ __device__ long long cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a
   return ctotal;
 }
 
+// min over queue[b, e) of (degree << 32 | position - b); *ties = how many vertices of the slice
+// have that minimum degree.  Every CTA scans the whole slice (it is one BFS level, and this
+// keeps the replicated state identical).  Contains __syncthreads().
+template <typename I, typename N>
+__device__ unsigned long long cl_last_level_min(const RcmArgs<I, N> &a, ClSmem<I> &s,
+                                                const I *queue, int64_t b, int64_t e,
+                                                unsigned *ties) {
+  const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
+  unsigned long long best = ~0ull;
+  for (int64_t k = b + threadIdx.x; k < e; k += kNwBlock) {
+    const I v = __ldcg(queue + k);
+    const unsigned long long dg = (unsigned long long)(a.xadj[v + 1] - a.xadj[v]);
+    const unsigned long long key = (dg << 32) | (unsigned long long)(k - b);
+    best = key < best ? key : best;
+  }
+  best = warp_reduce_min(best);
+  __syncthreads();
+  if (lane == 0) s.red[wid] = best;
+  __syncthreads();
+  best = ~0ull;
+  for (int w = 0; w < kNwWarps; w++) best = s.red[w] < best ? s.red[w] : best;
+  const unsigned long long mind = best >> 32;
+  unsigned cnt = 0;
+  for (int64_t k = b + threadIdx.x; k < e; k += kNwBlock) {
+    const I v = __ldcg(queue + k);
+    cnt += (unsigned long long)(a.xadj[v + 1] - a.xadj[v]) == mind ? 1u : 0u;
+  }
+  cnt = warp_reduce_sum(cnt);
+  if (lane == 0) s.wtot[wid] = cnt;
+  __syncthreads();
+  cnt = 0;
+  for (int w = 0; w < kNwWarps; w++) cnt += s.wtot[w];
+  __syncthreads();
+  *ties = cnt;
+  return best;
+}
+
 template <typename I, typename N>
 __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a) {
   extern __shared__ __align__(16) unsigned char nw_smem_raw[];
@@ -611,6 +651,7 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
           s.S.rlevel = -1;
           s.S.qlevel = 0;
           s.S.phase = PH_PBFS_INIT;
+          s.S.spec = 0;
           s.S.stat_components++;
         } else {
           s.S.next_i = base + (int64_t)kNwBlock * kFindPer;
@@ -691,34 +732,35 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
       const int64_t qlevel = ecc > s.S.qlevel ? ecc : s.S.qlevel;
       int next;  // phase after the mark reset
       int64_t new_root = s.S.root;
+      bool speculate = false;
       if (visited == qlevel + 1) {
         next = PH_CM_INIT;  // :58  path-like component: r is the root
       } else if (s.S.rlevel != qlevel) {
         // :62-78  eccentricity grew: min degree among the last level, first in queue order
         // (every CTA scans the whole level: it is short and this keeps the state replicated)
-        unsigned long long best = ~0ull;
-        for (int64_t k = s.S.prev_begin + threadIdx.x; k < s.S.lvl_begin; k += kNwBlock) {
-          const I v = a.Qp[k];
-          const unsigned long long dg = (unsigned long long)(a.xadj[v + 1] - a.xadj[v]);
-          const unsigned long long key = (dg << 32) | (unsigned long long)(k - s.S.prev_begin);
-          best = key < best ? key : best;
-        }
-        best = warp_reduce_min(best);
-        if (lane == 0) s.red[wid] = best;
-        __syncthreads();
-        best = ~0ull;
-        for (int w = 0; w < kNwWarps; w++) best = s.red[w] < best ? s.red[w] : best;
+        unsigned ties;
+        const unsigned long long best =
+            cl_last_level_min<I, N>(a, s, a.Qp, s.S.prev_begin, s.S.lvl_begin, &ties);
         new_root = (int64_t)a.Qp[s.S.prev_begin + (int64_t)(best & 0xffffffffull)];
-        next = PH_PBFS_INIT;
+        // The next BFS of peripheral() starts from new_root.  If its eccentricity does not
+        // exceed qlevel, peripheral() returns new_root and the Cuthill-McKee BFS walks the same
+        // component from the same root: both traversals have the same level SETS, so the CM
+        // BFS alone gives the eccentricity.  Run it first, speculatively; PH_CM_END checks the
+        // outcome and, when the eccentricity did grow, continues the literal sequence.
+        speculate = !a.no_spec;
+        next = speculate ? PH_CM_INIT : PH_PBFS_INIT;
       } else {
         next = PH_CM_INIT;  // :34  eccentricity did not grow: keep r
       }
       __syncthreads();
       if (threadIdx.x == 0) {
+        s.S.spec = speculate ? 1 : 0;
+        if (speculate) s.S.rlevel = qlevel;  // :35 of the iteration the CM BFS stands in for
         s.S.qlevel = qlevel;
         s.S.new_root_pending = new_root;
         s.S.next_phase_after_reset = next;
         s.S.phase = PH_PBFS_AFTER_RESET;
+        s.S.reset_cm = 0;
       }
       __syncthreads();
       // un-visit everything this BFS touched (mark[] doubles as distance[] and V[])
@@ -747,6 +789,55 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
       // component = Q[qst, lvl_end); reversed slice + final inversion (:147-160):
       // inv[Q[k]] = qst + (end-1-k)
       const int64_t qst = s.S.qst, end = s.S.lvl_end;
+      if (s.S.spec == 1) {
+        // this CM BFS stood in for a BFS of peripheral() (see PH_PBFS_END): rcm_reorder.cc:42-59
+        const int64_t visited = end - qst, ecc = s.S.depth - 1;
+        const int64_t qlevel = ecc > s.S.qlevel ? ecc : s.S.qlevel;
+        const bool confirmed = visited == qlevel + 1 || qlevel == s.S.rlevel;
+        if (!confirmed) {
+          // The eccentricity grew: peripheral() picks the min-degree vertex of the last level,
+          // FIRST IN FIFO ORDER on ties (:64-76).  The CM order of the level differs from the
+          // FIFO order, but the level SET is the same: when one vertex alone has the minimum
+          // degree it is the new root whatever the order, and the search continues (again
+          // speculatively) from it.  On a tie the FIFO order is needed: replay this BFS literally.
+          unsigned ties;
+          const unsigned long long best =
+              cl_last_level_min<I, N>(a, s, a.Q, s.S.prev_begin, s.S.lvl_begin, &ties);
+          const int64_t new_root = (int64_t)a.Q[s.S.prev_begin + (int64_t)(best & 0xffffffffull)];
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            if (ties == 1) {
+              s.S.stat_spec_chain++;
+              s.S.qlevel = qlevel;
+              s.S.rlevel = qlevel;
+              s.S.new_root_pending = new_root;
+              s.S.next_phase_after_reset = PH_CM_INIT;  // spec stays 1
+            } else {
+              s.S.stat_spec_fail++;
+              s.S.spec = 0;
+              s.S.new_root_pending = s.S.root;  // same root; rlevel/qlevel as before
+              s.S.next_phase_after_reset = PH_PBFS_INIT;
+            }
+            s.S.phase = PH_PBFS_AFTER_RESET;
+            s.S.reset_cm = 1;
+          }
+          __syncthreads();
+          if (visited > kBulkThreshold) {
+            if (threadIdx.x == 0) s.S.status = ST_NEED_RESET;
+            break;
+          }
+          for (int64_t k = qst + (int64_t)rank * kNwBlock + threadIdx.x; k < end;
+               k += (int64_t)C * kNwBlock)
+            atomicExch(&a.mark[a.Q[k]], kUnvisited);
+          cluster.sync();
+          continue;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          s.S.spec = 0;
+          s.S.stat_spec_ok++;
+        }
+      }
       __syncthreads();
       if (threadIdx.x == 0) {
         s.S.qwp = end;
@@ -985,6 +1076,10 @@ void rcm_impl(Workspace &ws, int64_t n, int64_t nnz, const N *xadj, const I *adj
   a.inv = out_inv;
   a.state = ws.alloc<RcmState>(1);
   a.force_wide = force_wide;
+  {
+    const char *ns = getenv("SB200_RCM_NO_SPEC");
+    a.no_spec = ns && ns[0] == '1';
+  }
   SB_CUDA(cudaMemsetAsync(a.mark, 0xff, n * sizeof(unsigned), st));
   RcmState S;
   memset(&S, 0, sizeof(S));
@@ -1068,9 +1163,9 @@ void rcm_impl(Workspace &ws, int64_t n, int64_t nnz, const N *xadj, const I *adj
         rcm_wide_level<I, N>(ws, a, w, S, cm);
       } while (S.lvl_end - S.lvl_begin > (force_wide ? 0 : narrow_cap));
     } else if (S.status == ST_NEED_RESET) {
-      const int64_t cnt = S.lvl_end;
-      SB_LAUNCH((rcm_reset_kernel<I>), (unsigned)ceil_div(cnt, 256), 256, 0, st, (const I *)a.Qp,
-                cnt, a.mark, kUnvisited);
+      const int64_t from = S.reset_cm ? S.qst : 0, cnt = S.lvl_end - from;
+      SB_LAUNCH((rcm_reset_kernel<I>), (unsigned)ceil_div(cnt, 256), 256, 0, st,
+                (const I *)(S.reset_cm ? a.Q : a.Qp) + from, cnt, a.mark, kUnvisited);
     } else if (S.status == ST_NEED_INVERT) {
       const int64_t cnt = S.lvl_end - S.qst;
       SB_LAUNCH((rcm_invert_kernel<I>), (unsigned)ceil_div(cnt, 256), 256, 0, st, (const I *)a.Q,
@@ -1119,6 +1214,15 @@ int sb200_rcm_last_stats(int64_t *h_out4) {
   h_out4[1] = g_last_rcm_stats.stat_levels_wide;
   h_out4[2] = g_last_rcm_stats.stat_bfs;
   h_out4[3] = g_last_rcm_stats.stat_components;
+  return SB200_OK;
+}
+
+// {speculative CM traversals confirmed, continued from a unique new root, replayed literally}
+int sb200_rcm_last_speculation(int64_t *h_out3) {
+  if (!h_out3) return SB200_ERR_BAD_ARG;
+  h_out3[0] = g_last_rcm_stats.stat_spec_ok;
+  h_out3[1] = g_last_rcm_stats.stat_spec_chain;
+  h_out3[2] = g_last_rcm_stats.stat_spec_fail;
   return SB200_OK;
 }
 

@@ -65,31 +65,170 @@ __global__ void permute1d_kernel(const V *__restrict__ vals, const I *__restrict
 
 // ---------------------------------------------------------------- DegreeReorder
 // Rank of vertex u in the order (degree ascending, id DESCENDING) -- the reference fills each
-// degree bucket from its end (degree_reorder.cc:42-46).  Keys = degrees, laid out so that the
-// stable sort sees ids in descending order: slot p holds vertex n-1-p.
-template <typename I, typename N>
-__global__ void degree_keys_kernel(const N *__restrict__ row_ptr, int64_t n,
-                                   uint32_t *__restrict__ keys32, uint64_t *__restrict__ keys64,
-                                   I *__restrict__ ids, unsigned long long *__restrict__ max_deg) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long d = 0;
-  if (p < n) {
-    const int64_t u = n - 1 - p;
-    d = (unsigned long long)(row_ptr[u + 1] - row_ptr[u]);
-    if (keys32) keys32[p] = (uint32_t)d;
-    if (keys64) keys64[p] = (uint64_t)d;
-    ids[p] = (I)u;
-  }
-  d = warp_reduce_max(d);
-  if (lane_id() == 0 && d > 0) atomicMax(max_deg, d);
+// degree bucket from its end (degree_reorder.cc:42-46).  Slot p of the sort input holds vertex
+// n-1-p, so that a STABLE sort by degree sees ids in descending order.
+//
+// Almost every vertex of a sparse matrix has a small degree, so the sort is one stable 256-way
+// partition on the digit min(degree, 255), computed straight from row_ptr (no key / id arrays
+// are materialised):
+//   upsweep    per-chunk digit histograms                        reads row_ptr once
+//   spine scan (scan.cuh)
+//   downsweep  stable rank of every slot inside its bin; bins 0..254 hold one degree each, so
+//              that rank is final and inv[n-1-p] is written directly (coalesced: ids are
+//              monotone in p).  Slots of bin 255 (degree >= 255) go, in stable order, to a
+//              compact (degree, id) list                          reads row_ptr, writes inv
+//   tail       the compact list (a tiny fraction of n) is sorted by degree with the general
+//              radix sort and ranked behind the first 255 bins.
+// HBM traffic for a low-degree matrix: 2 * (n+1) * N + n * I  vs  (n+1) * N + n * I compulsory.
+constexpr int kDgBlock = 256;
+constexpr int kDgWarps = kDgBlock / 32;
+constexpr int kDgIpt = 8;
+constexpr int kDgTile = kDgBlock * kDgIpt;
+constexpr int kDgBins = 256;
+
+struct DgChunking {
+  int64_t n, tiles;
+  int nchunks;
+  __host__ __device__ int64_t tile_begin(int c) const { return tiles * c / nchunks; }
+  __host__ __device__ int64_t tile_end(int c) const { return tiles * (c + 1) / nchunks; }
+};
+
+template <typename N>
+__device__ __forceinline__ unsigned long long dg_degree(const N *__restrict__ row_ptr, int64_t n,
+                                                        int64_t p) {
+  const int64_t u = n - 1 - p;
+  return (unsigned long long)(row_ptr[u + 1] - row_ptr[u]);
 }
 
-// inv[sorted[pos]] = ascending ? pos : n-1-pos   (degree_reorder.cc:47-57)
+template <typename N>
+__global__ void __launch_bounds__(kDgBlock)
+    degree_upsweep_kernel(const N *__restrict__ row_ptr, DgChunking ch,
+                          int64_t *__restrict__ spine, unsigned long long *__restrict__ max_deg) {
+  __shared__ unsigned hist[kDgWarps][kDgBins];
+  __shared__ unsigned long long s_max[kDgWarps];
+  const unsigned wid = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kDgWarps * kDgBins; i += kDgBlock) (&hist[0][0])[i] = 0;
+  __syncthreads();
+  const int c = blockIdx.x;
+  const int64_t begin = ch.tile_begin(c) * kDgTile;
+  int64_t end = ch.tile_end(c) * kDgTile;
+  if (end > ch.n) end = ch.n;
+  unsigned long long mx = 0;
+  for (int64_t base = begin; base < end; base += (int64_t)kDgBlock * 4) {
+    unsigned long long d[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int64_t p = base + k * kDgBlock + threadIdx.x;
+      d[k] = p < end ? dg_degree(row_ptr, ch.n, p) : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int64_t p = base + k * kDgBlock + threadIdx.x;
+      if (p < end) {
+        mx = d[k] > mx ? d[k] : mx;
+        // warp-aggregated: one shared-memory atomic per distinct digit among the lanes
+        const unsigned dig = d[k] < 255ull ? (unsigned)d[k] : 255u;
+        const unsigned peers = __match_any_sync(__activemask(), dig);
+        if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[wid][dig], (unsigned)__popc(peers));
+      }
+    }
+  }
+  mx = warp_reduce_max(mx);
+  if (lane_id() == 0) s_max[wid] = mx;
+  __syncthreads();
+  for (int b = threadIdx.x; b < kDgBins; b += kDgBlock) {
+    unsigned sum = 0;
+#pragma unroll
+    for (int w = 0; w < kDgWarps; w++) sum += hist[w][b];
+    spine[(int64_t)b * ch.nchunks + c] = sum;
+  }
+  if (threadIdx.x == 0) {  // one atomic per CTA, and only when it raises the maximum
+    mx = 0;
+    for (int w = 0; w < kDgWarps; w++) mx = s_max[w] > mx ? s_max[w] : mx;
+    if (mx > *reinterpret_cast<volatile unsigned long long *>(max_deg)) atomicMax(max_deg, mx);
+  }
+}
+
+// inv[id] = ascending ? pos : n-1-pos   (degree_reorder.cc:47-57)
+template <typename I, typename N, typename HK>
+__global__ void __launch_bounds__(kDgBlock)
+    degree_downsweep_kernel(const N *__restrict__ row_ptr, DgChunking ch,
+                            const int64_t *__restrict__ spine, int ascending,
+                            I *__restrict__ inv, HK *__restrict__ high_key,
+                            I *__restrict__ high_id) {
+  __shared__ unsigned cnt[kDgWarps][kDgBins];
+  __shared__ int64_t bin_off[kDgBins];
+  __shared__ int64_t high_base;
+  const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
+  const int c = blockIdx.x;
+  const int64_t n = ch.n;
+  bin_off[threadIdx.x] = spine[(int64_t)threadIdx.x * ch.nchunks + c];  // kDgBlock == kDgBins
+  if (threadIdx.x == 0) high_base = spine[(int64_t)255 * ch.nchunks];
+  for (int64_t tile = ch.tile_begin(c); tile < ch.tile_end(c); tile++) {
+    const int64_t warp_base = tile * kDgTile + (int64_t)wid * (kDgIpt * 32);
+    for (int i = threadIdx.x; i < kDgWarps * kDgBins; i += kDgBlock) (&cnt[0][0])[i] = 0;
+    unsigned long long d[kDgIpt];
+#pragma unroll
+    for (int r = 0; r < kDgIpt; r++) {
+      const int64_t p = warp_base + r * 32 + lane;
+      d[r] = p < n ? dg_degree(row_ptr, n, p) : 0ull;
+    }
+    __syncthreads();
+    // stable rank inside the warp: rounds in order, lanes in order
+    unsigned lp[kDgIpt];
+#pragma unroll
+    for (int r = 0; r < kDgIpt; r++) {
+      const bool valid = warp_base + r * 32 + lane < n;
+      const unsigned dig = valid ? (d[r] < 255ull ? (unsigned)d[r] : 255u) : 0xffffffffu;
+      const unsigned peers = __match_any_sync(0xffffffffu, dig);
+      const int leader = __ffs(peers) - 1;
+      unsigned base = 0;
+      if ((int)lane == leader && valid) {
+        base = cnt[wid][dig];
+        cnt[wid][dig] = base + __popc(peers);
+      }
+      base = __shfl_sync(0xffffffffu, base, leader);
+      lp[r] = base + __popc(peers & lanemask_lt());
+      __syncwarp();
+    }
+    __syncthreads();
+    {  // per digit: exclusive scan over the warps, advance the chunk's running bin offsets
+      const int b = threadIdx.x;
+      unsigned run = 0;
+#pragma unroll
+      for (int w = 0; w < kDgWarps; w++) {
+        const unsigned t = cnt[w][b];
+        cnt[w][b] = run;
+        run += t;
+      }
+      // cnt[w][b] += old bin offset would need 64 bits; keep them apart
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < kDgIpt; r++) {
+        const int64_t p = warp_base + r * 32 + lane;
+        if (p < n) {
+          const unsigned dig = d[r] < 255ull ? (unsigned)d[r] : 255u;
+          const int64_t pos = bin_off[dig] + cnt[wid][dig] + lp[r];
+          const int64_t u = n - 1 - p;
+          if (dig < 255u) {
+            inv[u] = (I)(ascending ? pos : n - 1 - pos);
+          } else {
+            high_key[pos - high_base] = (HK)d[r];
+            high_id[pos - high_base] = (I)u;
+          }
+        }
+      }
+      __syncthreads();
+      bin_off[b] += run;
+    }
+  }
+}
+
 template <typename I>
-__global__ void degree_rank_kernel(const I *__restrict__ sorted, int64_t n, int ascending,
-                                   I *__restrict__ inv) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < n) inv[sorted[p]] = (I)(ascending ? p : n - 1 - p);
+__global__ void degree_rank_kernel(const I *__restrict__ sorted, int64_t cnt, int64_t base,
+                                   int64_t n, int ascending, I *__restrict__ inv) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < cnt) inv[sorted[q]] = (I)(ascending ? base + q : n - 1 - (base + q));
 }
 
 template <typename I, typename N>
@@ -97,32 +236,48 @@ void degree_reorder_impl(Workspace &ws, int64_t n, const N *row_ptr, bool ascend
   if (n <= 0) return;
   cudaStream_t st = ws.stream();
   using UI = typename std::make_unsigned<I>::type;
-  const bool wide = sizeof(N) == 8;  // degrees may exceed 32 bits only with 64-bit nnz
-  uint32_t *k32 = wide ? nullptr : ws.alloc<uint32_t>(n);
-  uint64_t *k64 = wide ? ws.alloc<uint64_t>(n) : nullptr;
-  UI *ids = ws.alloc<UI>(n);
+  using HK = typename std::conditional<sizeof(N) == 8, uint64_t, uint32_t>::type;
+  const DeviceInfo &di = device_info(ws.device());
+  DgChunking ch;
+  ch.n = n;
+  ch.tiles = ceil_div(n, kDgTile);
+  const int64_t max_chunks = (int64_t)di.sm_count * 8;
+  ch.nchunks = (int)(ch.tiles < max_chunks ? ch.tiles : max_chunks);
+  const int64_t spine_len = (int64_t)kDgBins * ch.nchunks;
+  int64_t *spine_in = ws.alloc<int64_t>(spine_len + 1);
+  int64_t *spine = ws.alloc<int64_t>(spine_len + 1);
   unsigned long long *max_deg = ws.alloc<unsigned long long>(1);
   SB_CUDA(cudaMemsetAsync(max_deg, 0, sizeof(unsigned long long), st));
-  SB_LAUNCH((degree_keys_kernel<I, N>), map_grid(n), kMapBlock, 0, st, row_ptr, n, k32, k64,
-            (I *)ids, max_deg);
+  SB_LAUNCH((degree_upsweep_kernel<N>), ch.nchunks, kDgBlock, 0, st, row_ptr, ch, spine_in,
+            max_deg);
+  exclusive_scan<int64_t>(ws, LoadFn<int64_t>{spine_in}, spine, spine_len);
+  // the vertices of bin 255 (degree >= 255): how many, and how wide their degrees are
   unsigned long long h_max = 0;
+  int64_t h_base = 0;
   SB_CUDA(cudaMemcpyAsync(&h_max, max_deg, sizeof(h_max), cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(&h_base, spine + (int64_t)255 * ch.nchunks, sizeof(h_base),
+                          cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
-  std::vector<RsBitRange> ranges = {{0, bits_for(h_max)}};
-  const int P = n > 1 ? rs_num_passes(ranges) : 0;
-  UI *ids_out = ws.alloc<UI>(n);
-  UI *ids_tmp = P > 1 ? ws.alloc<UI>(n) : nullptr;
-  if (wide) {
-    uint64_t *ko = ws.alloc<uint64_t>(n), *kt = P > 1 ? ws.alloc<uint64_t>(n) : nullptr;
-    radix_sort<uint64_t, UI, NoVal>(ws, {k64, ids, nullptr}, {ko, ids_out, nullptr},
-                                    {kt, ids_tmp, nullptr}, n, ranges);
-  } else {
-    uint32_t *ko = ws.alloc<uint32_t>(n), *kt = P > 1 ? ws.alloc<uint32_t>(n) : nullptr;
-    radix_sort<uint32_t, UI, NoVal>(ws, {k32, ids, nullptr}, {ko, ids_out, nullptr},
-                                    {kt, ids_tmp, nullptr}, n, ranges);
+  const int64_t n_high = n - h_base;
+  HK *hk = n_high > 0 ? ws.alloc<HK>(n_high) : nullptr;
+  UI *hid = n_high > 0 ? ws.alloc<UI>(n_high) : nullptr;
+  SB_LAUNCH((degree_downsweep_kernel<I, N, HK>), ch.nchunks, kDgBlock, 0, st, row_ptr, ch,
+            (const int64_t *)spine, ascending ? 1 : 0, out_inv, hk, (I *)hid);
+  if (n_high <= 0) return;
+  const UI *sorted = hid;
+  if (h_max > 255ull && n_high > 1) {
+    // stable sort of the tail by degree; degrees below 255 do not occur here, so the low 8 bits
+    // still matter (255 vs 256 ...) and the full width is sorted
+    std::vector<RsBitRange> ranges = {{0, bits_for(h_max)}};
+    const int P = rs_num_passes(ranges);
+    HK *ko = ws.alloc<HK>(n_high), *kt = P > 1 ? ws.alloc<HK>(n_high) : nullptr;
+    UI *io = ws.alloc<UI>(n_high), *it = P > 1 ? ws.alloc<UI>(n_high) : nullptr;
+    radix_sort<HK, UI, NoVal>(ws, {hk, hid, nullptr}, {ko, io, nullptr}, {kt, it, nullptr}, n_high,
+                              ranges);
+    sorted = io;
   }
-  SB_LAUNCH((degree_rank_kernel<I>), map_grid(n), kMapBlock, 0, st, (const I *)ids_out, n,
-            ascending ? 1 : 0, out_inv);
+  SB_LAUNCH((degree_rank_kernel<I>), map_grid(n_high), kMapBlock, 0, st, (const I *)sorted, n_high,
+            h_base, n, ascending ? 1 : 0, out_inv);
 }
 
 // ---------------------------------------------------------------- Permute2D

@@ -23,7 +23,9 @@ SYMBOLS = [
     "sb200_free_host", "sb200_memcpy_h2d", "sb200_memcpy_d2h", "sb200_memcpy_d2d",
     "sb200_stream_synchronize", "sb200_coo_sort", "sb200_compressed_sort", "sb200_coo_to_csr",
     "sb200_csr_to_coo", "sb200_coo_to_csc", "sb200_csr_to_csc", "sb200_degree_reorder",
-    "sb200_rcm_reorder", "sb200_rcm_last_stats", "sb200_rcm_last_cycles", "sb200_permute2d", "sb200_permute1d", "sb200_inverse_permutation",
+    "sb200_rcm_reorder", "sb200_rcm_last_stats", "sb200_rcm_last_cycles",
+    "sb200_rcm_last_speculation", "sb200_permute2d", "sb200_permute1d",
+    "sb200_inverse_permutation",
     "sb200_degrees", "sb200_degree_distribution", "sb200_partition_rows", "sb200_launch_count",
     "sb200_reset_launch_count", "sb200_coo_to_csr_block", "sb200_csr_to_csc_block",
     "sb200_exclusive_scan", "sb200_rank_keys", "sb200_max_degree", "sb200_degree_histogram",
@@ -190,6 +192,9 @@ def rcm_last_stats():
     _check(load().sb200_rcm_last_cycles(cyc))
     d["phase_cycles"] = dict(zip(("seek", "claim", "barrier1", "recheck", "compact", "exchange",
                                   "sort_write", "rescan"), list(cyc)))
+    spec = (ctypes.c_int64 * 3)()
+    _check(load().sb200_rcm_last_speculation(spec))
+    d["spec_confirmed"], d["spec_continued"], d["spec_replayed"] = (int(x) for x in spec)
     return d
 
 

@@ -410,3 +410,37 @@ def test_permute2d_short_rows_kernel(sb, orc):
         got = sb.permute2d(n, n, dev(rp), dev(cc2), dev(vv2), dev(order), dev(order))
         for a, b, what in zip(got, exp, ("row_ptr", "col", "vals")):
             assert eq(host(a), b), f"short-row permute2d {what} {idt} {nt} {vt}"
+
+
+def _sparse_forest(n, seed, ppv=0.6):
+    rng = np.random.default_rng(seed)
+    e = rng.integers(0, n, size=(int(n * ppv), 2))
+    rr, cc = np.concatenate([e[:, 0], e[:, 1]]), np.concatenate([e[:, 1], e[:, 0]])
+    key = np.unique(rr.astype(np.int64) * n + cc)
+    return n, (key // n).astype(np.int32), (key % n).astype(np.int32)
+
+
+def test_rcm_speculative_peripheral(sb, orc, monkeypatch):
+    """peripheral()'s BFS traversals after the first run as the Cuthill-McKee traversal itself
+    (rcm.cu PH_PBFS_END / PH_CM_END): confirmed, continued from a unique new root, or replayed
+    literally -- always the reference's permutation, with and without the speculation."""
+    seen = {"spec_confirmed": 0, "spec_continued": 0, "spec_replayed": 0}
+    graphs_ = [_sparse_forest(3000, 11), _sparse_forest(20000, 12, 0.8), graphs.er(2000, 2, seed=5),
+               graphs.multi_component(), graphs.rmat(10, 4, seed=3)]
+    for n, row, col in graphs_:
+        rp = graphs.csr_of(n, row, col)
+        exp = orc.rcm_reorder(n, rp, col)
+        for force_wide in ("0", "1"):
+            monkeypatch.setenv("SB200_RCM_FORCE_WIDE", force_wide)
+            monkeypatch.setenv("SB200_RCM_NO_SPEC", "0")
+            got = host(sb.rcm_reorder(n, dev(rp), dev(col)))
+            assert eq(got, exp), f"rcm (speculative) mismatch at {np.flatnonzero(got != exp)[:10]}"
+            st = sb.rcm_last_stats()
+            for k in seen:
+                seen[k] += st[k]
+            monkeypatch.setenv("SB200_RCM_NO_SPEC", "1")
+            got = host(sb.rcm_reorder(n, dev(rp), dev(col)))
+            assert eq(got, exp)
+            st = sb.rcm_last_stats()
+            assert st["spec_confirmed"] == st["spec_continued"] == st["spec_replayed"] == 0
+    assert all(v > 0 for v in seen.values()), seen
