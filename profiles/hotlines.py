@@ -1,7 +1,7 @@
 """Per-source-line stall samples from an ncu report.
 
     ncu -i rep.ncu-rep --page source --print-source cuda,sass --csv -k regex:<kernel> > x.csv
-    python profiles/hotlines.py x.csv [top]
+    python profiles/hotlines.py x.csv [top] [inst]   # "inst": rank by executed instructions
 """
 import csv
 import sys
@@ -46,7 +46,8 @@ def main(path, top=30):
     tot = sum(a[0] for a in agg.values()) or 1
     toti = sum(a[1] for a in agg.values()) or 1
     print(f"samples {tot}  warp-instructions {toti}")
-    for (f, ln, src), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    by_inst = len(sys.argv) > 3 and sys.argv[3] == "inst"
+    for (f, ln, src), a in sorted(agg.items(), key=lambda kv: -kv[1][1 if by_inst else 0])[:top]:
         st = ",".join(f"{k[6:]}:{v}" for k, v in sorted(a[2].items(), key=lambda kv: -kv[1])[:3])
         print(f"{100 * a[0] / tot:5.1f}% {100 * a[1] / toti:5.1f}%i {f}:{ln:<4d} {src[:70]:70s} [{st}]")
 

@@ -65,7 +65,14 @@ FN = {
     "permute2d_rand": lambda: lib.permute2d(n, n, rp, col, vals, perm, perm),
     "coo_sort": coo_sort,
     "rcm": lambda: lib.rcm_reorder(n, rp, col),
+    "csr_to_coo": lambda: lib.csr_to_coo(n, n, rp, col, vals),
 }
+if "permute2d_rcm" in args.ops:
+    rcm_perm = lib.rcm_reorder(n, rp, col)
+    FN["permute2d_rcm"] = lambda: lib.permute2d(n, n, rp, col, vals, rcm_perm, rcm_perm)
+if "permute2d_deg" in args.ops:
+    deg_perm = lib.degree_reorder(n, rp, True)
+    FN["permute2d_deg"] = lambda: lib.permute2d(n, n, rp, col, vals, deg_perm, deg_perm)
 out = {"graph": args.graph, "size": args.size, "n": n, "nnz": nnz,
        "env": {k: v for k, v in os.environ.items() if k.startswith("SB200_")}}
 for op in args.ops.split(","):

@@ -409,58 +409,91 @@ __global__ void ex_tile_bounds_kernel(const N *__restrict__ ptr, int64_t n_seg, 
 }
 
 // Window t covers output positions [t*kExTile, (t+1)*kExTile).  Segments starting inside the
-// window mark their first position; an inclusive max-scan spreads the segment id; positions
-// before the first mark belong to the segment that straddles the window start (r0 - 1).
+// window mark their first position with (r - r0 + 1); an inclusive max-scan spreads the mark;
+// positions before the first mark belong to the segment that straddles the window start
+// (r0 - 1).  Every thread owns 8 consecutive positions: marks are zeroed, scanned and turned
+// into row ids in registers, and each output array is written with two 16-byte stores per
+// thread (4-byte ids; the copies of col / vals move the same way).
+template <typename T>
+__device__ __forceinline__ void ex_copy8(const T *__restrict__ src, T *__restrict__ dst, int64_t w0,
+                                         int q0, int count) {
+  if (q0 + 8 <= count && ((reinterpret_cast<uintptr_t>(src + w0) |
+                           reinterpret_cast<uintptr_t>(dst + w0)) & 15) == 0) {
+    constexpr int kVec = 16 / sizeof(T);
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src + w0 + q0);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst + w0 + q0);
+#pragma unroll
+    for (int k = 0; k < 8 / kVec; k++) __stcs(d4 + k, __ldcs(s4 + k));
+  } else {
+    for (int k = 0; k < 8 && q0 + k < count; k++)
+      st_stream(dst + w0 + q0 + k, ld_stream(src + w0 + q0 + k));
+  }
+}
+
 template <typename I, typename N, typename V>
 __global__ void __launch_bounds__(kExBlock)
     expand_ptr_kernel(const N *__restrict__ ptr, const int64_t *__restrict__ tile_seg,
                       int64_t nnz, const I *__restrict__ col, const V *__restrict__ vals,
                       I *__restrict__ out_row, I *__restrict__ out_col,
                       V *__restrict__ out_vals, I row_base) {
-  __shared__ long long mark[kExTile];
-  __shared__ long long warp_max[kExBlock / 32];
+  static_assert(kExTile == kExBlock * 8, "8 positions per thread");
+  __shared__ __align__(16) unsigned mark[kExTile];
+  __shared__ unsigned warp_max[kExBlock / 32];
   const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
   const int64_t t = blockIdx.x;
   const int64_t w0 = t * kExTile;
   const int count = (int)(nnz - w0 < kExTile ? nnz - w0 : kExTile);
   const int64_t r0 = tile_seg[t], r1 = tile_seg[t + 1];
-  for (int q = threadIdx.x; q < kExTile; q += kExBlock) mark[q] = -1;
-  __syncthreads();
-  for (int64_t r = r0 + threadIdx.x; r < r1; r += kExBlock) {
-    const int64_t b = ptr[r], e = ptr[r + 1];
-    if (e > b) mark[b - w0] = r;  // non-empty segments have distinct starts
+  const int q0 = threadIdx.x * 8;
+  uint4 *m4 = reinterpret_cast<uint4 *>(mark + q0);
+  m4[0] = make_uint4(0u, 0u, 0u, 0u);
+  m4[1] = make_uint4(0u, 0u, 0u, 0u);
+  // the copies do not depend on the row ids: get them in flight first
+  if (out_col) ex_copy8<I>(col, out_col, w0, q0, count);
+  if constexpr (has_val<V>) {
+    if (out_vals) ex_copy8<V>(vals, out_vals, w0, q0, count);
   }
   __syncthreads();
-  constexpr int kPer = kExTile / kExBlock;
-  const int q0 = threadIdx.x * kPer;
-  long long m = -1;
+  // r1 - r0 (segments starting in the window, empty ones included) < 2^32: checked by the host
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += kExBlock) {
+    const int64_t b = ptr[r], e = ptr[r + 1];
+    if (e > b) mark[b - w0] = (unsigned)(r - r0 + 1);  // non-empty segments: distinct starts
+  }
+  __syncthreads();
+  uint4 a = m4[0], c = m4[1];
+  unsigned h[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+  unsigned m = 0;
 #pragma unroll
-  for (int k = 0; k < kPer; k++) m = mark[q0 + k] > m ? mark[q0 + k] : m;
-  long long inc = m;
+  for (int k = 0; k < 8; k++) m = h[k] > m ? h[k] : m;
+  unsigned inc = m;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    long long tt = __shfl_up_sync(0xffffffffu, inc, o);
+    const unsigned tt = __shfl_up_sync(0xffffffffu, inc, o);
     if ((int)lane >= o) inc = tt > inc ? tt : inc;
   }
   if (lane == 31) warp_max[wid] = inc;
   __syncthreads();
-  long long run = r0 - 1;  // the segment straddling the window start
+  unsigned run = 0;  // 0 = the segment straddling the window start (r0 - 1)
   for (unsigned w = 0; w < wid; w++) run = warp_max[w] > run ? warp_max[w] : run;
-  long long prev = __shfl_up_sync(0xffffffffu, inc, 1);
+  const unsigned prev = __shfl_up_sync(0xffffffffu, inc, 1);
   if (lane > 0) run = prev > run ? prev : run;
+  I rows[8];
 #pragma unroll
-  for (int k = 0; k < kPer; k++) {
-    const long long h = mark[q0 + k];
-    run = h > run ? h : run;
-    mark[q0 + k] = run;
+  for (int k = 0; k < 8; k++) {
+    run = h[k] > run ? h[k] : run;
+    rows[k] = (I)(r0 - 1 + (int64_t)run) + row_base;
   }
-  __syncthreads();
-  for (int q = threadIdx.x; q < count; q += kExBlock) {
-    st_stream(out_row + w0 + q, (I)mark[q] + row_base);
-    if (out_col) st_stream(out_col + w0 + q, ld_stream(col + w0 + q));
-    if constexpr (has_val<V>) {
-      if (out_vals) st_stream(out_vals + w0 + q, ld_stream(vals + w0 + q));
-    }
+  if (q0 + 8 <= count && (reinterpret_cast<uintptr_t>(out_row + w0) & 15) == 0 &&
+      sizeof(I) == 4) {
+    uint4 *d4 = reinterpret_cast<uint4 *>(out_row + w0 + q0);
+    __stcs(d4, make_uint4((unsigned)rows[0], (unsigned)rows[1], (unsigned)rows[2],
+                          (unsigned)rows[3]));
+    __stcs(d4 + 1, make_uint4((unsigned)rows[4], (unsigned)rows[5], (unsigned)rows[6],
+                              (unsigned)rows[7]));
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (q0 + k < count) st_stream(out_row + w0 + q0 + k, rows[k]);
   }
 }
 
@@ -468,6 +501,8 @@ template <typename I, typename N, typename V>
 void expand_ptr(Workspace &ws, const N *ptr, int64_t n_seg, int64_t nnz, const I *col,
                 const V *vals, I *out_row, I *out_col, V *out_vals, I row_base = 0) {
   if (nnz <= 0) return;
+  SB_REQUIRE(n_seg < (1ll << 32) - 1, SB200_ERR_BAD_ARG,
+             "row expansion supports fewer than 2^32-1 segments (got %lld)", (long long)n_seg);
   cudaStream_t st = ws.stream();
   const int64_t ntiles = ceil_div(nnz, kExTile);
   int64_t *tile_seg = ws.alloc<int64_t>(ntiles + 1);

@@ -262,6 +262,252 @@ __global__ void __launch_bounds__(BLOCK, MINB)
   }
 }
 
+// ------------------------------------------------------------------ downsweep, bulk-copy pipeline
+// Same ranking and the same results as rs_downsweep_kernel, restructured around the load latency
+// that bounded it (ncu: 47 % of the stall samples were long-scoreboard waits on the tile's own
+// key / payload loads, issue rate 0.15 per scheduler):
+//   * the whole tile (keys + payloads, 12 B x 4096 records = 48 KB) is fetched by ONE thread with
+//     three 1-D bulk async copies (cp.async.bulk global -> shared, completion on an mbarrier);
+//     two stage buffers, so the copy of tile t+1 is in flight for the whole of tile t and no
+//     register is spent on prefetching;
+//   * a stage buffer is read into registers as soon as it lands and is then reused as the staging
+//     area in which the tile is laid out in digit order before the coalesced global writes;
+//   * all match_any instructions of a tile are issued back to back before the serial counter
+//     updates; warp-private counters are 16 bits (a tile has < 65536 records).
+// Tiles that cannot be bulk-copied (the partial last tile) are read with plain loads.
+__device__ __forceinline__ uint32_t rs_smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void rs_mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rs_smem_u32(bar)), "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void rs_mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rs_smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void rs_mbar_wait(uint64_t *bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(rs_smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void rs_bulk_g2s(void *dst, const void *src, unsigned bytes,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(rs_smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(rs_smem_u32(bar))
+      : "memory");
+}
+
+// Lanes holding the same 8-bit digit, from eight ballots.  MATCH.ANY has a data-dependent cost
+// (one step per distinct value in the warp; digits of a tile are almost all distinct) and was
+// 38 % of the stall samples of this kernel; VOTE is a fixed-latency instruction.
+__device__ __forceinline__ unsigned rs_match_digit(unsigned d) {
+  unsigned peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < kRsMaxBits; b++) {
+    const bool bit = (d & (1u << b)) != 0u;  // one LOP3 with a predicate result
+    const unsigned bal = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? bal : ~bal;
+  }
+  return peers;
+}
+
+template <int BLOCK, int IPT, typename K, typename V1, typename V2, typename Off>
+struct RsPipeSmem {
+  static constexpr int kTile = BLOCK * IPT;
+  using P1 = typename std::conditional<has_val<V1>, V1, char>::type;
+  using P2 = typename std::conditional<has_val<V2>, V2, char>::type;
+  __align__(16) K sk[2][kTile];
+  __align__(16) P1 s1[2][has_val<V1> ? kTile : 16];
+  __align__(16) P2 s2[2][has_val<V2> ? kTile : 16];
+  unsigned short cnt[BLOCK / 32][kRsMaxBins];
+  unsigned short excl[kRsMaxBins];
+  int64_t bin_off[kRsMaxBins];
+  Off delta[kRsMaxBins];
+  unsigned scan_scratch[34];
+  __align__(8) uint64_t bar[2];
+};
+
+template <int BLOCK, int IPT, int MINB, typename K, typename V1, typename V2, typename Off>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    rs_downsweep_pipe_kernel(const K *__restrict__ kin, K *__restrict__ kout,
+                             const V1 *__restrict__ v1in, V1 *__restrict__ v1out,
+                             const V2 *__restrict__ v2in, V2 *__restrict__ v2out, RsChunking ch,
+                             int shift, int bits, const int64_t *__restrict__ spine) {
+  using Smem = RsPipeSmem<BLOCK, IPT, K, V1, V2, Off>;
+  constexpr int kTile = BLOCK * IPT;
+  static_assert(kTile < 65536, "16-bit slot counters");
+  constexpr unsigned kTileBytes =
+      (unsigned)(kTile * (sizeof(K) + (has_val<V1> ? sizeof(V1) : 0) +
+                          (has_val<V2> ? sizeof(V2) : 0)));
+  extern __shared__ __align__(128) unsigned char rs_pipe_smem_raw[];
+  Smem &s = *reinterpret_cast<Smem *>(rs_pipe_smem_raw);
+  const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
+  const unsigned mask = (1u << bits) - 1u;
+  const int nbins = 1 << bits;
+  const int c = blockIdx.x;
+  const int64_t n = ch.n;
+  const int64_t t_begin = ch.tile_begin(c), t_end = ch.tile_end(c);
+  if (t_begin >= t_end) return;
+
+  auto issue = [&](int64_t tile, int st) {  // one thread
+    rs_mbar_expect_tx(&s.bar[st], kTileBytes);
+    const int64_t base = tile * kTile;
+    rs_bulk_g2s(s.sk[st], kin + base, (unsigned)(kTile * sizeof(K)), &s.bar[st]);
+    if constexpr (has_val<V1>)
+      rs_bulk_g2s(s.s1[st], v1in + base, (unsigned)(kTile * sizeof(V1)), &s.bar[st]);
+    if constexpr (has_val<V2>)
+      rs_bulk_g2s(s.s2[st], v2in + base, (unsigned)(kTile * sizeof(V2)), &s.bar[st]);
+  };
+  auto full = [&](int64_t tile) { return (tile + 1) * kTile <= n; };
+
+  if (threadIdx.x == 0) {
+    rs_mbar_init(&s.bar[0], 1);
+    rs_mbar_init(&s.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (full(t_begin)) issue(t_begin, 0);
+    if (t_begin + 1 < t_end && full(t_begin + 1)) issue(t_begin + 1, 1);
+  }
+  if ((int)threadIdx.x < nbins)
+    s.bin_off[threadIdx.x] = spine[(int64_t)threadIdx.x * ch.nchunks + c];
+  __syncthreads();  // barriers initialised before anybody waits on them
+
+  unsigned phase0 = 0, phase1 = 0;
+  for (int64_t tile = t_begin; tile < t_end; tile++) {
+    const int st = (int)((tile - t_begin) & 1);
+    const int64_t tile_base_idx = tile * kTile;
+    const int tile_count = full(tile) ? kTile : (int)(n - tile_base_idx);
+    const int local_base = (int)wid * (IPT * 32) + (int)lane;
+    K *const sk = s.sk[st];
+    [[maybe_unused]] typename Smem::P1 *const s1 = s.s1[st];
+    [[maybe_unused]] typename Smem::P2 *const s2 = s.s2[st];
+
+    if (tile_count == kTile) {
+      if (st == 0) {
+        rs_mbar_wait(&s.bar[0], phase0);
+        phase0 ^= 1u;
+      } else {
+        rs_mbar_wait(&s.bar[1], phase1);
+        phase1 ^= 1u;
+      }
+    } else {
+      // the partial last tile of the array: plain loads into the stage buffer, padded with
+      // all-ones keys.  Padding has the largest digit and comes last in the tile, so it ranks
+      // behind every real record (slots >= tile_count, never written) and only inflates the
+      // count of the last bin of the last tile, which nobody reads any more.
+      for (int q = threadIdx.x; q < kTile; q += BLOCK) {
+        if (q < tile_count) {
+          sk[q] = ld_stream(kin + tile_base_idx + q);
+          if constexpr (has_val<V1>) s1[q] = ld_stream(v1in + tile_base_idx + q);
+          if constexpr (has_val<V2>) s2[q] = ld_stream(v2in + tile_base_idx + q);
+        } else {
+          sk[q] = (K)~K(0);
+        }
+      }
+      __syncthreads();
+    }
+
+    K key[IPT];
+    [[maybe_unused]] typename Smem::P1 p1[IPT];
+    [[maybe_unused]] typename Smem::P2 p2[IPT];
+#pragma unroll
+    for (int r = 0; r < IPT; r++) {
+      const int q = local_base + r * 32;
+      key[r] = sk[q];
+      if constexpr (has_val<V1>) p1[r] = s1[q];
+      if constexpr (has_val<V2>) p2[r] = s2[q];
+    }
+    {
+      unsigned *z = reinterpret_cast<unsigned *>(&s.cnt[0][0]);
+#pragma unroll
+      for (int i = 0; i < (BLOCK / 32) * kRsMaxBins / 2 / BLOCK; i++) z[i * BLOCK + threadIdx.x] = 0;
+    }
+    // ---- 1a. all the matches of the tile, back to back ----
+    unsigned peers[IPT];
+#pragma unroll
+    for (int r = 0; r < IPT; r++) peers[r] = rs_match_digit(rs_digit(key[r], shift, mask));
+    __syncthreads();  // stage buffer is in registers everywhere; counters are zero
+
+    // ---- 1b. stable ranking inside the warp (rounds in order, lanes in order) ----
+    unsigned short *const my_cnt = s.cnt[wid];
+    unsigned lp[IPT];  // (rank inside the warp << 8) | digit
+#pragma unroll
+    for (int r = 0; r < IPT; r++) {
+      const unsigned d = rs_digit(key[r], shift, mask);
+      const int leader = __ffs(peers[r]) - 1;
+      unsigned base = 0;
+      if ((int)lane == leader) {
+        base = my_cnt[d];
+        my_cnt[d] = (unsigned short)(base + __popc(peers[r]));
+      }
+      base = __shfl_sync(0xffffffffu, base, leader);
+      lp[r] = ((base + __popc(peers[r] & lanemask_lt())) << 8) | d;
+      __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- 2. per digit: exclusive scan over warps, then exclusive scan over digits ----
+    unsigned hist = 0;
+    if ((int)threadIdx.x < nbins) {
+#pragma unroll
+      for (int w = 0; w < BLOCK / 32; w++) {
+        const unsigned t = s.cnt[w][threadIdx.x];
+        s.cnt[w][threadIdx.x] = (unsigned short)hist;
+        hist += t;
+      }
+    }
+    const unsigned excl = block_exclusive_scan(hist, s.scan_scratch);
+    if ((int)threadIdx.x < nbins) {
+      s.excl[threadIdx.x] = (unsigned short)excl;  // first tile-local slot of the digit
+      const int64_t off = s.bin_off[threadIdx.x];
+      s.delta[threadIdx.x] = (Off)(off - (int64_t)excl);
+      s.bin_off[threadIdx.x] = off + hist;
+    }
+    __syncthreads();
+
+    // ---- 3. lay the tile out in digit order in the (now free) stage buffer ----
+#pragma unroll
+    for (int r = 0; r < IPT; r++) {
+      const unsigned d = lp[r] & 0xffu;
+      const unsigned at = (lp[r] >> 8) + my_cnt[d] + s.excl[d];
+      sk[at] = key[r];
+      if constexpr (has_val<V1>) s1[at] = p1[r];
+      if constexpr (has_val<V2>) s2[at] = p2[r];
+    }
+    __syncthreads();
+
+    // ---- 4. coalesced runs to global memory (element index in Off: one IMAD.WIDE per array
+    //         when the array has fewer than 2^31 records) ----
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+      const int j = k * BLOCK + (int)threadIdx.x;
+      if (j < tile_count) {
+        const K kk = sk[j];
+        const Off dst = s.delta[rs_digit(kk, shift, mask)] + (Off)j;
+        kout[dst] = kk;
+        if constexpr (has_val<V1>) v1out[dst] = s1[j];
+        if constexpr (has_val<V2>) v2out[dst] = s2[j];
+      }
+    }
+    __syncthreads();  // the stage buffer has been read; it may be overwritten by the next copy
+    if (threadIdx.x == 0 && tile + 2 < t_end && full(tile + 2)) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(tile + 2, st);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host driver
 struct RsBitRange {
   int begin, end;  // sort on key bits [begin, end)
@@ -315,8 +561,42 @@ void rs_launch_downsweep(cudaStream_t st, RsBufs<K, V1, V2> src, RsBufs<K, V1, V
   }
 }
 
-// Downsweep configuration: 512 threads x 8 records (4096-record tile, two CTAs per SM, 32
-// resident warps).  SB200_RS_CONFIG selects the alternatives kept for tuning runs.
+// One launch of the bulk-copy pipelined downsweep (inputs must be 16-byte aligned).  Records
+// narrow enough for two resident CTAs per SM are compiled for 64 registers; wider ones (one
+// CTA per SM by shared memory anyway) get the full register file.
+template <int BLOCK, int IPT, typename K, typename V1, typename V2, typename Off>
+void rs_launch_downsweep_pipe_off(cudaStream_t st, RsBufs<K, V1, V2> src, RsBufs<K, V1, V2> dst,
+                                  const RsChunking &ch, int shift, int bits,
+                                  const int64_t *spine) {
+  constexpr int smem = (int)sizeof(RsPipeSmem<BLOCK, IPT, K, V1, V2, Off>);
+  constexpr int MINB = (smem <= 112 * 1024 && BLOCK <= 512) ? 2 : 1;
+  auto kern = rs_downsweep_pipe_kernel<BLOCK, IPT, MINB, K, V1, V2, Off>;
+  SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  SB_LAUNCH(kern, ch.nchunks, BLOCK, smem, st, (const K *)src.k, dst.k, (const V1 *)src.v1,
+            dst.v1, (const V2 *)src.v2, dst.v2, ch, shift, bits, spine);
+}
+template <int BLOCK, int IPT, typename K, typename V1, typename V2>
+void rs_launch_downsweep_pipe(cudaStream_t st, RsBufs<K, V1, V2> src, RsBufs<K, V1, V2> dst,
+                              const RsChunking &ch, int shift, int bits, const int64_t *spine) {
+  if (ch.n < (1ll << 31))
+    rs_launch_downsweep_pipe_off<BLOCK, IPT, K, V1, V2, int32_t>(st, src, dst, ch, shift, bits,
+                                                                 spine);
+  else
+    rs_launch_downsweep_pipe_off<BLOCK, IPT, K, V1, V2, int64_t>(st, src, dst, ch, shift, bits,
+                                                                 spine);
+}
+
+template <typename K, typename V1, typename V2>
+inline bool rs_bulk_aligned(const RsBufs<K, V1, V2> &b) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(b.k);
+  if constexpr (has_val<V1>) a |= reinterpret_cast<uintptr_t>(b.v1);
+  if constexpr (has_val<V2>) a |= reinterpret_cast<uintptr_t>(b.v2);
+  return (a & 15) == 0;
+}
+
+// Downsweep configuration.  Default (0): bulk-copy pipelined kernel, 512 threads x 8 records
+// (4096-record tile, two CTAs per SM).  SB200_RS_CONFIG = 10..14 select the register-prefetch
+// kernel in the shapes kept for tuning runs; it is also the route for unaligned inputs.
 inline int rs_config() {
   static const int cfg = [] {
     const char *e = getenv("SB200_RS_CONFIG");
@@ -324,12 +604,22 @@ inline int rs_config() {
   }();
   return cfg;
 }
+inline int rs_chunks_per_sm() {
+  static const int v = [] {
+    const char *e = getenv("SB200_RS_CHUNKS_PER_SM");
+    const int x = e ? atoi(e) : 4;
+    return x > 0 ? x : 4;
+  }();
+  return v;
+}
 inline int rs_config_tile(int cfg) {
   switch (cfg) {
-    case 1: return 256 * 12;
-    case 2: return 512 * 12;
-    case 3: return 384 * 10;
-    case 4: return 256 * 16;
+    case 11: return 256 * 12;
+    case 12: return 512 * 12;
+    case 13: return 384 * 10;
+    case 14: return 256 * 16;
+    case 1: return 256 * 16;
+    case 2: return 512 * 6;
     default: return 512 * 8;
   }
 }
@@ -357,7 +647,7 @@ void radix_sort(Workspace &ws, RsBufs<K, V1, V2> in, RsBufs<K, V1, V2> out,
   ch.n = n;
   ch.tile = rs_config_tile(cfg);
   ch.tiles = ceil_div(n, ch.tile);
-  int64_t max_chunks = (int64_t)di.sm_count * 4;
+  int64_t max_chunks = (int64_t)di.sm_count * rs_chunks_per_sm();
   ch.nchunks = (int)(ch.tiles < max_chunks ? ch.tiles : max_chunks);
   int64_t *spine_in = ws.alloc<int64_t>((int64_t)kRsMaxBins * ch.nchunks + 1);
   int64_t *spine = ws.alloc<int64_t>((int64_t)kRsMaxBins * ch.nchunks + 1);
@@ -375,14 +665,21 @@ void radix_sort(Workspace &ws, RsBufs<K, V1, V2> in, RsBufs<K, V1, V2> out,
                 bits, spine_in);
       exclusive_scan<int64_t>(ws, LoadFn<int64_t>{spine_in}, spine,
                               (int64_t)(1 << bits) * ch.nchunks);
-      if (cfg == 1)
+      const bool bulk = rs_bulk_aligned(src);
+      if (cfg == 11)
         rs_launch_downsweep<256, 12, 2, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
-      else if (cfg == 2)
+      else if (cfg == 12)
         rs_launch_downsweep<512, 12, 1, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
-      else if (cfg == 3)
+      else if (cfg == 13)
         rs_launch_downsweep<384, 10, 2, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
-      else if (cfg == 4)
+      else if (cfg == 14)
         rs_launch_downsweep<256, 16, 2, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
+      else if (cfg == 1 && bulk)
+        rs_launch_downsweep_pipe<256, 16, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
+      else if (cfg == 2 && bulk)
+        rs_launch_downsweep_pipe<512, 6, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
+      else if (cfg == 0 && bulk)
+        rs_launch_downsweep_pipe<512, 8, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
       else
         rs_launch_downsweep<512, 8, 2, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
       src = dst;

@@ -285,40 +285,84 @@ void degree_reorder_impl(Workspace &ws, int64_t n, const N *row_ptr, bool ascend
 // row, the source offset of its first entry and its length; the scan and the gather kernels
 // then read both arrays coalesced (no dependent irow -> xadj gathers inside the hot kernels).
 // The same pass finds the longest row, which selects the gather kernel.
+// (source offset, length) of a new row, written and read as one word
+template <typename N>
+struct alignas(2 * sizeof(N)) RowRec {
+  N base, len;
+};
+template <typename N>
+struct RowLenFn {
+  const RowRec<N> *rec;
+  __device__ N operator()(int64_t i) const { return rec[i].len; }
+};
+constexpr int kPrepRows = 4;  // rows per thread: independent row_order loads in flight
 template <typename I, typename N>
-__global__ void permute_prepare_kernel(const N *__restrict__ xadj, const I *__restrict__ row_order,
-                                       int64_t n, int64_t *__restrict__ src_base,
-                                       N *__restrict__ new_len,
-                                       unsigned long long *__restrict__ max_len) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kMapBlock)
+    permute_prepare_kernel(const N *__restrict__ xadj, const I *__restrict__ row_order, int64_t n,
+                           RowRec<N> *__restrict__ rec,
+                           unsigned long long *__restrict__ max_len, int64_t near_rows) {
+  // max_len[0]: longest row.  max_len[1]: number of old rows i whose successor i+1 lands within
+  // near_rows new rows of it -- when most do, rows that are neighbours in the SOURCE are gathered
+  // close in time and the gather kernel may ask L2 for whole lines (see ld_gather_l2_128).
+  const int64_t i0 = (int64_t)blockIdx.x * (kMapBlock * kPrepRows) + threadIdx.x;
+  int64_t j[kPrepRows];
+  N b[kPrepRows], e[kPrepRows];
+#pragma unroll
+  for (int u = 0; u < kPrepRows; u++) {
+    const int64_t i = i0 + u * kMapBlock;
+    if (i < n) {
+      j[u] = row_order ? (int64_t)row_order[i] : i;
+      b[u] = xadj[i];
+      e[u] = xadj[i + 1];
+    }
+  }
   unsigned long long len = 0;
-  if (i < n) {
-    const int64_t j = row_order ? (int64_t)row_order[i] : i;
-    const N b = xadj[i], e = xadj[i + 1];
-    src_base[j] = (int64_t)b;
-    new_len[j] = e - b;
-    len = (unsigned long long)(e - b);
+  unsigned near = 0;
+#pragma unroll
+  for (int u = 0; u < kPrepRows; u++) {
+    const int64_t i = i0 + u * kMapBlock;
+    const int64_t jn = __shfl_down_sync(0xffffffffu, i < n ? j[u] : (int64_t)0, 1);
+    if (i + 1 < n && lane_id() < 31) {
+      const int64_t d = jn > j[u] ? jn - j[u] : j[u] - jn;
+      near += d <= near_rows ? 1u : 0u;
+    }
+    if (i < n) {
+      rec[j[u]] = RowRec<N>{b[u], (N)(e[u] - b[u])};  // one scattered store per row
+      const unsigned long long l = (unsigned long long)(e[u] - b[u]);
+      len = l > len ? l : len;
+    }
   }
   // one atomic per CTA, and only when it would raise the maximum (same-address atomics
   // serialise in L2: one per warp cost 0.25 ms at 16.7 M rows)
-  __shared__ unsigned long long s_max[kMapBlock / 32];
-  len = warp_reduce_max(len);
-  if (lane_id() == 0) s_max[threadIdx.x >> 5] = len;
+  __shared__ unsigned long long s_max;
+  __shared__ unsigned s_near;
+  if (threadIdx.x == 0) {
+    s_max = 0;
+    s_near = 0;
+  }
+  __syncthreads();
+  near = __reduce_add_sync(0xffffffffu, near);
+  if (lane_id() == 0 && near > 0) atomicAdd(&s_near, near);
+  if (__all_sync(0xffffffffu, len < (1ull << 32)))
+    len = __reduce_max_sync(0xffffffffu, (unsigned)len);
+  else
+    len = warp_reduce_max(len);
+  if (lane_id() == 0 && len > 0) atomicMax(&s_max, len);
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned long long mx = 0;
-    for (int w = 0; w < kMapBlock / 32; w++) mx = s_max[w] > mx ? s_max[w] : mx;
+    const unsigned long long mx = s_max;
     if (mx > *reinterpret_cast<volatile unsigned long long *>(max_len)) atomicMax(max_len, mx);
+    if (s_near > 0) atomicAdd(max_len + 1, (unsigned long long)s_near);
   }
 }
 
 template <typename I, typename N, typename V>
 struct GatherLoader {
-  const int64_t *src_base;  // per new row: offset of the old row's first entry
+  const RowRec<N> *rec;  // per new row: offset of the old row's first entry (+ its length)
   const I *adj;
   const V *vals;
   const I *col_order;  // old col -> new col, or null
-  __device__ int64_t seg_base(int64_t r) const { return src_base[r]; }
+  __device__ int64_t seg_base(int64_t r) const { return (int64_t)rec[r].base; }
   // default cache policy on purpose: a gathered row shares its 32-byte sectors with the rows
   // next to it in the SOURCE, which are gathered a little later (evict-first loads made HBM
   // deliver those sectors twice)
@@ -354,93 +398,108 @@ __device__ __forceinline__ void short_cex(I &ka, V &va, I &kb, V &vb) {
   }
 }
 
-template <typename I, typename N, typename V>
-__global__ void __launch_bounds__(kSrBlock)
-    permute_short_rows_kernel(const int64_t *__restrict__ src_base,
-                              const N *__restrict__ out_ptr, const I *__restrict__ adj,
-                              const V *__restrict__ vals, const I *__restrict__ col_order,
-                              int64_t n, I *__restrict__ out_col, V *__restrict__ out_vals) {
+template <typename I, typename N, typename V, int MINB, bool PROMOTE>
+__global__ void __launch_bounds__(kSrBlock, MINB)
+    permute_short_rows_kernel(const RowRec<N> *__restrict__ rec, const N *__restrict__ out_ptr,
+                              const I *__restrict__ adj, const V *__restrict__ vals,
+                              const I *__restrict__ col_order, int64_t n,
+                              I *__restrict__ out_col, V *__restrict__ out_vals) {
   using VR = typename std::conditional<has_val<V>, V, char>::type;
   __shared__ I stage_k[kSrBlock / 32][32 * kShortRow];
   __shared__ VR stage_v[kSrBlock / 32][has_val<V> ? 32 * kShortRow : 1];
+  __shared__ unsigned char stage_own[kSrBlock / 32][32 * kShortRow];
   const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
   I *sk = stage_k[wid];
   [[maybe_unused]] VR *sv = stage_v[wid];
+  unsigned char *own = stage_own[wid];
   const int64_t nbatches = (n + 31) >> 5;
   const int64_t wstride = ((int64_t)gridDim.x * kSrBlock) >> 5;
   for (int64_t bt = (((int64_t)blockIdx.x * kSrBlock) >> 5) + wid; bt < nbatches; bt += wstride) {
     const int64_t j = (bt << 5) + lane;
-    int64_t ob = 0, p = 0;
+    N ob = 0, p = 0;
     unsigned len = 0;
     if (j < n) {
-      ob = (int64_t)out_ptr[j];
-      len = (unsigned)((int64_t)out_ptr[j + 1] - ob);
-      p = src_base[j];
+      const RowRec<N> rr = rec[j];
+      ob = out_ptr[j];
+      len = (unsigned)rr.len;
+      p = rr.base;
     }
-    const int64_t ob0 = __shfl_sync(0xffffffffu, ob, 0);
+    const N ob0 = __shfl_sync(0xffffffffu, ob, 0);
     const unsigned incl = warp_inclusive_scan(len);
     const unsigned excl = incl - len;  // == ob - ob0 for the rows that exist
     const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-    // ---- fetch in concatenated order ----
-    for (unsigned base = 0; base < total; base += 32) {
-      const unsigned sidx = base + lane;
-      unsigned owner = 0;  // number of lanes whose inclusive end <= sidx
+    // every row tells its slots of the concatenated batch who owns them
 #pragma unroll
-      for (int step = 16; step > 0; step >>= 1) {
-        const unsigned val = __shfl_sync(0xffffffffu, incl, (owner + step - 1) & 31);
-        if (val <= sidx) owner += step;
-      }
-      owner &= 31;
-      const int64_t p_o = __shfl_sync(0xffffffffu, p, owner);
+    for (int u = 0; u < kShortRow; u++)
+      if ((unsigned)u < len) own[excl + u] = (unsigned char)lane;
+    __syncwarp();
+    // ---- fetch in concatenated order: all the loads of the batch are issued before the
+    //      first dependent renumbering gather, all the gathers before the first use ----
+    I c[kShortRow];
+    [[maybe_unused]] VR cv[kShortRow];
+#pragma unroll
+    for (int u = 0; u < kShortRow; u++) {
+      const unsigned sidx = u * 32 + lane;
+      const unsigned owner = sidx < total ? own[sidx] : 0u;
+      const N p_o = __shfl_sync(0xffffffffu, p, owner);
       const unsigned ex_o = __shfl_sync(0xffffffffu, excl, owner);
       if (sidx < total) {
-        const int64_t src = p_o + (int64_t)(sidx - ex_o);
-        I c = __ldg(adj + src);
-        if constexpr (has_val<V>) sv[sidx] = __ldg(vals + src);
-        if (col_order) c = col_order[c];
-        sk[sidx] = c;
+        const N src = p_o + (N)(sidx - ex_o);
+        if constexpr (PROMOTE) {
+          c[u] = ld_gather_l2_128(adj + src);
+          if constexpr (has_val<V>) cv[u] = ld_gather_l2_128(vals + src);
+        } else {
+          c[u] = __ldg(adj + src);
+          if constexpr (has_val<V>) cv[u] = __ldg(vals + src);
+        }
+      }
+    }
+    if (col_order) {
+#pragma unroll
+      for (int u = 0; u < kShortRow; u++)
+        if (u * 32 + lane < total) c[u] = col_order[c[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < kShortRow; u++) {
+      const unsigned sidx = u * 32 + lane;
+      if (sidx < total) {
+        sk[sidx] = c[u];
+        if constexpr (has_val<V>) sv[sidx] = cv[u];
       }
     }
     __syncwarp();
-    // ---- the owning lane sorts its row in registers ----
-    I k[kShortRow];
-    [[maybe_unused]] VR v[kShortRow];
+    // ---- rank of every entry inside its row (rows have <= kShortRow entries, all staged in
+    //      this warp's slice); the entry goes straight to its sorted place.  The 32 rows are
+    //      adjacent in the output, so the warp still writes one contiguous run. ----
 #pragma unroll
     for (int u = 0; u < kShortRow; u++) {
-      k[u] = std::numeric_limits<I>::max();  // padding sorts to the end
-      if constexpr (has_val<V>) v[u] = V(0);
-      if ((unsigned)u < len) {
-        k[u] = sk[excl + u];
-        if constexpr (has_val<V>) v[u] = sv[excl + u];
-      }
-    }
-    // Batcher odd-even merge sort for 8 keys (19 compare-exchanges)
-#define SB_CEX(a, b)                                          \
-  if constexpr (has_val<V>)                                   \
-    short_cex<I, V>(k[a], v[a], k[b], v[b]);                  \
-  else {                                                      \
-    NoVal nv1, nv2;                                           \
-    short_cex<I, NoVal>(k[a], nv1, k[b], nv2);                \
-  }
-    SB_CEX(0, 1) SB_CEX(2, 3) SB_CEX(4, 5) SB_CEX(6, 7)
-    SB_CEX(0, 2) SB_CEX(1, 3) SB_CEX(4, 6) SB_CEX(5, 7)
-    SB_CEX(1, 2) SB_CEX(5, 6)
-    SB_CEX(0, 4) SB_CEX(1, 5) SB_CEX(2, 6) SB_CEX(3, 7)
-    SB_CEX(2, 4) SB_CEX(3, 5)
-    SB_CEX(1, 2) SB_CEX(3, 4) SB_CEX(5, 6)
-#undef SB_CEX
+      const unsigned sidx = u * 32 + lane;
+      const unsigned owner = sidx < total ? own[sidx] : 0u;
+      const unsigned ex_o = __shfl_sync(0xffffffffu, excl, owner);
+      const unsigned len_o = __shfl_sync(0xffffffffu, len, owner);
+      if (sidx < total) {
+        const I k = c[u];
+        unsigned rank = 0;
 #pragma unroll
-    for (int u = 0; u < kShortRow; u++) {
-      if ((unsigned)u < len) {
-        sk[excl + u] = k[u];
-        if constexpr (has_val<V>) sv[excl + u] = v[u];
+        for (int t = 0; t < kShortRow; t++) {
+          if ((unsigned)t < len_o) {
+            const I kj = sk[ex_o + t];
+            bool before = kj < k;
+            if (kj == k) {  // duplicate column ids: (col, val) order, then position (csr.cc:147)
+              const unsigned jj = ex_o + t;
+              if constexpr (has_val<V>) {
+                const V vj = sv[jj];
+                before = vj < cv[u] || (!(cv[u] < vj) && jj < sidx);
+              } else {
+                before = jj < sidx;
+              }
+            }
+            rank += before ? 1u : 0u;
+          }
+        }
+        st_stream(out_col + ob0 + ex_o + rank, k);
+        if constexpr (has_val<V>) st_stream(out_vals + ob0 + ex_o + rank, (V)cv[u]);
       }
-    }
-    __syncwarp();
-    // ---- one contiguous run of the output ----
-    for (unsigned sidx = lane; sidx < total; sidx += 32) {
-      st_stream(out_col + ob0 + sidx, sk[sidx]);
-      if constexpr (has_val<V>) st_stream(out_vals + ob0 + sidx, (V)sv[sidx]);
     }
     __syncwarp();
   }
@@ -451,29 +510,44 @@ void permute2d_impl(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const N *x
                     const I *adj, const V *vals, const I *row_order, const I *col_order,
                     N *out_row_ptr, I *out_col, V *out_vals) {
   cudaStream_t st = ws.stream();
-  int64_t *src_base = ws.alloc<int64_t>(n + 1);
-  N *new_len = ws.alloc<N>(n + 1);
-  unsigned long long *max_len = ws.alloc<unsigned long long>(1);
-  SB_CUDA(cudaMemsetAsync(max_len, 0, sizeof(unsigned long long), st));
+  RowRec<N> *rec = ws.alloc<RowRec<N>>(n + 1);
+  unsigned long long *max_len = ws.alloc<unsigned long long>(2);
+  SB_CUDA(cudaMemsetAsync(max_len, 0, 2 * sizeof(unsigned long long), st));
+  // "near": within 32 MB worth of gathered rows (a quarter of the L2)
+  const int64_t row_bytes = n > 0 ? (nnz / n + 1) * (int64_t)(sizeof(I) + (has_val<V> ? sizeof(V) : 0)) : 1;
+  const int64_t near_rows = (32ll << 20) / row_bytes;
   if (n > 0)
-    SB_LAUNCH((permute_prepare_kernel<I, N>), map_grid(n), kMapBlock, 0, st, xadj, row_order, n,
-              src_base, new_len, max_len);
-  exclusive_scan<N>(ws, LoadFn<N>{new_len}, out_row_ptr, n);
+    SB_LAUNCH((permute_prepare_kernel<I, N>), map_grid(n, kPrepRows), kMapBlock, 0, st, xadj,
+              row_order, n, rec, max_len, near_rows);
+  exclusive_scan<N>(ws, RowLenFn<N>{rec}, out_row_ptr, n);
   if (n <= 0 || nnz <= 0) return;
-  unsigned long long h_max = 0;
-  SB_CUDA(cudaMemcpyAsync(&h_max, max_len, sizeof(h_max), cudaMemcpyDeviceToHost, st));
+  unsigned long long h_stats[2] = {0, 0};
+  SB_CUDA(cudaMemcpyAsync(h_stats, max_len, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
+  const unsigned long long h_max = h_stats[0];
   if (h_max <= (unsigned long long)kShortRow) {
     // one 32-row batch per warp, CTAs in row order: neighbouring rows are in flight at the
     // same time, so the sectors they share (20-byte rows in 32-byte sectors, nearby col_order
     // entries) are fetched from HBM once.  (A grid-stride loop over a capped grid spreads the
     // resident warps over distant row ranges and doubled the DRAM read traffic.)
-    SB_LAUNCH((permute_short_rows_kernel<I, N, V>), (unsigned)ceil_div(n, (int64_t)kSrBlock), kSrBlock,
-              0, st, (const int64_t *)src_base, (const N *)out_row_ptr, adj, vals, col_order, n,
-              out_col, out_vals);
+    static const int promote_env = [] {
+      const char *e = getenv("SB200_P2D_PROMOTE");  // tuning: 0 = never, 1 = always
+      return e ? atoi(e) : -1;
+    }();
+    const bool promote =
+        promote_env >= 0 ? promote_env != 0 : (row_order != nullptr && 2 * h_stats[1] >= (unsigned long long)n);
+    const unsigned grid = (unsigned)ceil_div(n, (int64_t)kSrBlock);
+    if (promote)
+      SB_LAUNCH((permute_short_rows_kernel<I, N, V, 5, true>), grid, kSrBlock, 0, st,
+                (const RowRec<N> *)rec, (const N *)out_row_ptr, adj, vals, col_order, n, out_col,
+                out_vals);
+    else
+      SB_LAUNCH((permute_short_rows_kernel<I, N, V, 5, false>), grid, kSrBlock, 0, st,
+                (const RowRec<N> *)rec, (const N *)out_row_ptr, adj, vals, col_order, n, out_col,
+                out_vals);
     return;
   }
-  GatherLoader<I, N, V> ld{src_base, adj, vals, col_order};
+  GatherLoader<I, N, V> ld{rec, adj, vals, col_order};
   segmented_sort<I, N, V>(ws, ld, (const N *)out_row_ptr, n, m, nnz, out_col, out_vals);
 }
 

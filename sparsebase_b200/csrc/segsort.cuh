@@ -209,11 +209,9 @@ __global__ void __launch_bounds__(kSsBlock)
     const int len = s.len[sb];
     if (len > kSsEnum) continue;
     const I k = s.key[q];
-    int rank = 0;
-    for (int j = sb; j < sb + len; j++) {
-      const I kj = s.key[j];
-      rank += (kj < k || (kj == k && j < q)) ? 1 : 0;
-    }
+    int rank = 0;  // entries before q count when <=, entries after q when < (stable)
+    for (int j = sb; j < q; j++) rank += s.key[j] <= k ? 1 : 0;
+    for (int j = q + 1; j < sb + len; j++) rank += s.key[j] < k ? 1 : 0;
     out_idx[first + sb + rank] = k;
     if constexpr (has_val<V>) out_val[first + sb + rank] = s.val[q];
   }
