@@ -47,6 +47,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the Permute2D kernels of this workload,
+    per launch, from the committed `ncu --set full` capture (profiles/*_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "r1_e_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get("permute2d_dram_bytes_per_launch")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -300,6 +310,45 @@ def main():
         time_op("degree_distribution", lambda: lib.degree_distribution(n, nnz, row_ptr))
         del row
 
+    # ---- N > 1: the row-block sharded operators on the same matrix (strong scaling: the C2
+    #      matrix split into `world` nnz-balanced row blocks; max time over ranks, exchanges
+    #      included; aggregate roofline = world x per-GPU peak) ----
+    ops_sharded = None
+    if world > 1:
+        from sparsebase_b200 import sharded
+        bounds = lib.partition_rows(n, nnz, row_ptr, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        a, b = int(row_ptr[lo]), int(row_ptr[hi])
+        deg_l = (row_ptr[lo + 1:hi + 1] - row_ptr[lo:hi]).to(torch.int64)
+        row_l = torch.repeat_interleave(torch.arange(lo, hi, device=dev, dtype=torch.int32), deg_l)
+        col_l, val_l = col[a:b].contiguous(), vals[a:b].contiguous()
+        shard = sharded.coo_to_csr(lib, n, n, bounds, row_l.clone(), col_l.clone(), val_l.clone())
+        ops_sharded = {}
+
+        def time_sharded(name, fn, reps=3):
+            fn()
+            barrier()
+            e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e_a.record()
+            for _ in range(reps):
+                fn()
+            e_b.record()
+            barrier()
+            t = torch.tensor([e_a.elapsed_time(e_b) / reps], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            gbs = ALG_BYTES[name](n, nnz) / (ms * 1e-3) / 1e9
+            ops_sharded[name] = {"ms": ms, "gnnz_per_s": nnz / (ms * 1e-3) / 1e9,
+                                 "alg_gb_per_s": gbs, "roofline_frac": gbs / (peak * world)}
+
+        time_sharded("coo_to_csr", lambda: sharded.coo_to_csr(lib, n, n, bounds, row_l, col_l,
+                                                              val_l, copy=False))
+        time_sharded("csr_to_csc", lambda: sharded.csr_to_csc(lib, shard))
+        time_sharded("permute2d", lambda: sharded.permute2d(lib, shard, inv, inv))
+        time_sharded("degree_reorder", lambda: sharded.degree_reorder(lib, shard, True))
+        time_sharded("degree_distribution", lambda: sharded.degree_distribution(lib, shard))
+        del row_l, col_l, val_l, shard
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -323,15 +372,21 @@ def main():
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "ss_tile_kernel (fused gather/renumber/row-sort of "
-                     "Permute2D) + its 3 helper kernels", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": "permute_short_rows_kernel (fused gather / "
+                     "renumber / row-sort of Permute2D) + permute_prepare_kernel + "
+                     "scan_lookback_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": p2d_bytes,
                      "note": "RCM (rcm_narrow_kernel) is latency-bound level walking and is "
                              "reported in ms (rcm_ms), not against the HBM roofline"},
         "ops": ops,
     }
+    if ops_sharded is not None:
+        line["ops_sharded"] = ops_sharded
+        line["ops_sharded_note"] = ("row-block sharded operators on the same C2 matrix split over "
+                                    f"{world} GPUs (strong scaling), exchanges included, max over "
+                                    "ranks; roofline_frac is against world x per-GPU peak")
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_reference_step(args.cpu_grid)
         line["cpu_baseline"] = {"value": cb["value"], "unit": "GNNZ/s", "cores": cb["cores"],

@@ -84,6 +84,7 @@ int guarded(int device, Fn &&fn) {
 struct DeviceInfo {
   int sm_count;
   int max_smem_optin;
+  int64_t l2_bytes;
 };
 const DeviceInfo &device_info(int device);
 
@@ -244,23 +245,6 @@ __device__ __forceinline__ T ld_stream(const T *p) {
 template <typename T>
 __device__ __forceinline__ void st_stream(T *p, T v) {
   __stcs(p, v);
-}
-
-// Gather load that asks L2 to fetch the whole 128-byte line on a miss.  For gathers whose
-// neighbouring sectors are wanted a little later (by other warps), this turns four 32-byte DRAM
-// reads spread over time into one 128-byte burst; the later requests hit in L2.
-template <typename T>
-__device__ __forceinline__ T ld_gather_l2_128(const T *p) {
-  static_assert(sizeof(T) == 4 || sizeof(T) == 8, "4- or 8-byte elements");
-  if constexpr (sizeof(T) == 4) {
-    unsigned v;
-    asm volatile("ld.global.nc.L2::128B.b32 %0, [%1];" : "=r"(v) : "l"(p));
-    return *reinterpret_cast<T *>(&v);
-  } else {
-    unsigned long long v;
-    asm volatile("ld.global.nc.L2::128B.b64 %0, [%1];" : "=l"(v) : "l"(p));
-    return *reinterpret_cast<T *>(&v);
-  }
 }
 
 }  // namespace sb200

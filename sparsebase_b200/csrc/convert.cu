@@ -28,13 +28,59 @@ namespace sb200 {
 constexpr int kBfBlock = 256;
 constexpr int kBfIpt = 4;
 
+// A run of more than kGapMax empty segments (isolated vertices, or the columns a row block of
+// a sharded matrix never touches) is not filled by the one thread that sees the boundary: it
+// is appended to a list and filled afterwards by gap_fill_kernel with the whole grid.  (One
+// thread filling 8.4 M trailing entries cost 30 ms in the row-block CSR->CSC.)
+constexpr int kGapMax = 32;
+constexpr int kGapWarpMax = 8192;  // longer gaps are filled by all CTAs together
+struct GapRec {
+  int64_t lo, hi;  // ptr[lo..hi] = value
+  int64_t value;
+};
+struct GapList {
+  GapRec *rec;
+  unsigned *count;
+  unsigned cap;  // exact bound for a sorted stream; a stream with inversions may overrun it,
+                 // and its ptr is rebuilt by the histogram path anyway
+};
+template <typename N>
+__device__ __forceinline__ void fill_or_defer(N *__restrict__ ptr, int64_t lo, int64_t hi,
+                                              int64_t value, const GapList &gl) {
+  if (hi - lo >= kGapMax) {
+    const unsigned k = atomicAdd(gl.count, 1u);
+    if (k < gl.cap) gl.rec[k] = GapRec{lo, hi, value};
+  } else {
+    for (int64_t r = lo; r <= hi; r++) ptr[r] = (N)value;
+  }
+}
+template <typename N>
+__global__ void __launch_bounds__(256) gap_fill_kernel(GapList gl, N *__restrict__ ptr) {
+  const unsigned cnt = *gl.count < gl.cap ? *gl.count : gl.cap;
+  const unsigned lane = lane_id();
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t k = warp; k < cnt; k += nwarps) {  // medium gaps: one warp each
+    const GapRec g = gl.rec[k];
+    if (g.hi - g.lo >= kGapWarpMax) continue;
+    for (int64_t r = g.lo + lane; r <= g.hi; r += 32) ptr[r] = (N)g.value;
+  }
+  for (unsigned k = 0; k < cnt; k++) {  // long gaps (at most n / kGapWarpMax): whole grid
+    const GapRec g = gl.rec[k];
+    if (g.hi - g.lo < kGapWarpMax) continue;
+    for (int64_t r = g.lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= g.hi;
+         r += (int64_t)gridDim.x * blockDim.x)
+      ptr[r] = (N)g.value;
+  }
+}
+
 template <typename I, typename N, typename V>
 __global__ void __launch_bounds__(kBfBlock)
     boundary_fill_copy_kernel(const I *__restrict__ idx, const I *__restrict__ sec,
                               const V *__restrict__ vals, int64_t nnz, int64_t n_seg,
                               I idx_base, N *__restrict__ ptr, I *__restrict__ out_sec,
                               V *__restrict__ out_vals, unsigned *__restrict__ flags,
-                              int64_t start) {
+                              int64_t start, GapList gl) {
   const int64_t base = start + ((int64_t)blockIdx.x * kBfBlock) * kBfIpt;
   bool inv = false, sec_unsorted = false;
   I my[kBfIpt], prev[kBfIpt], ms[kBfIpt], ps[kBfIpt];
@@ -69,9 +115,8 @@ __global__ void __launch_bounds__(kBfBlock)
       int64_t hi = (int64_t)my[k];
       if (hi >= n_seg) hi = n_seg - 1;  // indices >= n_seg are not representable (see header)
       if (lo < 0) lo = 0;
-      for (int64_t r = lo; r <= hi; r++) ptr[r] = (N)i;
-      if (i == nnz - 1)
-        for (int64_t r = (int64_t)my[k] + 1; r <= n_seg; r++) ptr[r] = (N)nnz;
+      fill_or_defer<N>(ptr, lo, hi, i, gl);
+      if (i == nnz - 1) fill_or_defer<N>(ptr, (int64_t)my[k] + 1 < 0 ? 0 : (int64_t)my[k] + 1, n_seg, nnz, gl);
     }
   }
   if (__any_sync(0xffffffffu, inv) && lane_id() == 0) atomicOr(&flags[0], 1u);
@@ -92,7 +137,7 @@ __global__ void __launch_bounds__(kBvBlock)
                                   const V *__restrict__ vals, int64_t nnz, int64_t ngroups,
                                   int64_t n_seg, I idx_base, N *__restrict__ ptr,
                                   I *__restrict__ out_sec, V *__restrict__ out_vals,
-                                  unsigned *__restrict__ flags) {
+                                  unsigned *__restrict__ flags, GapList gl) {
   constexpr int kPer = 16 / sizeof(I);      // elements per 16-byte word
   constexpr int E = kBvLoads * kPer;        // elements per thread
   using VR = typename std::conditional<has_val<V>, V, I>::type;
@@ -159,10 +204,9 @@ __global__ void __launch_bounds__(kBvBlock)
         int64_t hi = (int64_t)my;
         if (hi >= n_seg) hi = n_seg - 1;
         if (lo < 0) lo = 0;
-        for (int64_t r = lo; r <= hi; r++) ptr[r] = (N)i;
+        fill_or_defer<N>(ptr, lo, hi, i, gl);
       }
-      if (i == nnz - 1)
-        for (int64_t r = (int64_t)my + 1; r <= n_seg; r++) ptr[r] = (N)nnz;
+      if (i == nnz - 1) fill_or_defer<N>(ptr, (int64_t)my + 1 < 0 ? 0 : (int64_t)my + 1, n_seg, nnz, gl);
       p = my;
     }
   }
@@ -214,6 +258,12 @@ void build_ptr_and_copy(Workspace &ws, const I *idx, const I *sec, const V *vals
     h_flags[0] = h_flags[1] = 0;
     return;
   }
+  // every deferred gap covers more than kGapMax segments of [0, n_seg], so this bounds the list
+  GapList gl;
+  gl.cap = (unsigned)((n_seg + 1) / kGapMax + 2);
+  gl.rec = ws.alloc<GapRec>(gl.cap);
+  gl.count = ws.alloc<unsigned>(1);
+  SB_CUDA(cudaMemsetAsync(gl.count, 0, sizeof(unsigned), st));
   // 16-byte path for the bulk, scalar path for the tail (or everything if unaligned)
   constexpr int kE = kBvLoads * (16 / (int)sizeof(I));
   auto aligned16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -223,15 +273,16 @@ void build_ptr_and_copy(Workspace &ws, const I *idx, const I *sec, const V *vals
     const int64_t ngroups = nnz / kE;
     SB_LAUNCH((boundary_fill_copy_vec_kernel<I, N, V>), (unsigned)ceil_div(ngroups, kBvBlock),
               kBvBlock, 0, st, idx, sec, vals, nnz, ngroups, n_seg, idx_base, ptr, out_sec,
-              out_vals, flags);
+              out_vals, flags, gl);
     done = ngroups * kE;
   }
   if (done < nnz) {
     const int64_t per_block = (int64_t)kBfBlock * kBfIpt;
     SB_LAUNCH((boundary_fill_copy_kernel<I, N, V>), (unsigned)ceil_div(nnz - done, per_block),
               kBfBlock, 0, st, idx, sec, vals, nnz, n_seg, idx_base, ptr, out_sec, out_vals, flags,
-              done);
+              done, gl);
   }
+  SB_LAUNCH((gap_fill_kernel<N>), device_info(ws.device()).sm_count * 4, 256, 0, st, gl, ptr);
   SB_CUDA(cudaMemcpyAsync(h_flags, flags, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   if (h_flags[0]) {

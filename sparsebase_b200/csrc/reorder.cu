@@ -303,7 +303,8 @@ __global__ void __launch_bounds__(kMapBlock)
                            unsigned long long *__restrict__ max_len, int64_t near_rows) {
   // max_len[0]: longest row.  max_len[1]: number of old rows i whose successor i+1 lands within
   // near_rows new rows of it -- when most do, rows that are neighbours in the SOURCE are gathered
-  // close in time and the gather kernel may ask L2 for whole lines (see ld_gather_l2_128).
+  // close in time and share sectors in L2; when few do, the gathered rows are read with
+  // evict-first loads (GatherLoader::stream).
   const int64_t i0 = (int64_t)blockIdx.x * (kMapBlock * kPrepRows) + threadIdx.x;
   int64_t j[kPrepRows];
   N b[kPrepRows], e[kPrepRows];
@@ -362,13 +363,16 @@ struct GatherLoader {
   const I *adj;
   const V *vals;
   const I *col_order;  // old col -> new col, or null
+  bool stream;         // evict-first loads for the gathered rows
   __device__ int64_t seg_base(int64_t r) const { return (int64_t)rec[r].base; }
   // default cache policy on purpose: a gathered row shares its 32-byte sectors with the rows
   // next to it in the SOURCE, which are gathered a little later (evict-first loads made HBM
   // deliver those sectors twice)
-  __device__ I raw_key(int64_t p) const { return __ldg(adj + p); }
-  __device__ I map_key(I c) const { return col_order ? col_order[c] : c; }
-  __device__ V val(int64_t p) const { return __ldg(vals + p); }
+  // (`stream` is set when the permutation scatters source neighbours far apart: nothing is
+  // shared then, and evict-first keeps the gathered rows from displacing the col_order table)
+  __device__ I raw_key(int64_t p) const { return stream ? __ldcs(adj + p) : __ldg(adj + p); }
+  __device__ I map_key(I c) const { return col_order ? __ldg(col_order + c) : c; }
+  __device__ V val(int64_t p) const { return stream ? __ldcs(vals + p) : __ldg(vals + p); }
 };
 
 // ---- matrices whose rows all have <= kShortRow entries (stencils, meshes).  One warp owns
@@ -398,7 +402,7 @@ __device__ __forceinline__ void short_cex(I &ka, V &va, I &kb, V &vb) {
   }
 }
 
-template <typename I, typename N, typename V, int MINB, bool PROMOTE>
+template <typename I, typename N, typename V, int MINB>
 __global__ void __launch_bounds__(kSrBlock, MINB)
     permute_short_rows_kernel(const RowRec<N> *__restrict__ rec, const N *__restrict__ out_ptr,
                               const I *__restrict__ adj, const V *__restrict__ vals,
@@ -445,19 +449,14 @@ __global__ void __launch_bounds__(kSrBlock, MINB)
       const unsigned ex_o = __shfl_sync(0xffffffffu, excl, owner);
       if (sidx < total) {
         const N src = p_o + (N)(sidx - ex_o);
-        if constexpr (PROMOTE) {
-          c[u] = ld_gather_l2_128(adj + src);
-          if constexpr (has_val<V>) cv[u] = ld_gather_l2_128(vals + src);
-        } else {
-          c[u] = __ldg(adj + src);
-          if constexpr (has_val<V>) cv[u] = __ldg(vals + src);
-        }
+        c[u] = __ldg(adj + src);
+        if constexpr (has_val<V>) cv[u] = __ldg(vals + src);
       }
     }
     if (col_order) {
 #pragma unroll
       for (int u = 0; u < kShortRow; u++)
-        if (u * 32 + lane < total) c[u] = col_order[c[u]];
+        if (u * 32 + lane < total) c[u] = __ldg(col_order + c[u]);
     }
 #pragma unroll
     for (int u = 0; u < kShortRow; u++) {
@@ -530,24 +529,19 @@ void permute2d_impl(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const N *x
     // same time, so the sectors they share (20-byte rows in 32-byte sectors, nearby col_order
     // entries) are fetched from HBM once.  (A grid-stride loop over a capped grid spreads the
     // resident warps over distant row ranges and doubled the DRAM read traffic.)
-    static const int promote_env = [] {
-      const char *e = getenv("SB200_P2D_PROMOTE");  // tuning: 0 = never, 1 = always
-      return e ? atoi(e) : -1;
-    }();
-    const bool promote =
-        promote_env >= 0 ? promote_env != 0 : (row_order != nullptr && 2 * h_stats[1] >= (unsigned long long)n);
     const unsigned grid = (unsigned)ceil_div(n, (int64_t)kSrBlock);
-    if (promote)
-      SB_LAUNCH((permute_short_rows_kernel<I, N, V, 5, true>), grid, kSrBlock, 0, st,
-                (const RowRec<N> *)rec, (const N *)out_row_ptr, adj, vals, col_order, n, out_col,
-                out_vals);
-    else
-      SB_LAUNCH((permute_short_rows_kernel<I, N, V, 5, false>), grid, kSrBlock, 0, st,
-                (const RowRec<N> *)rec, (const N *)out_row_ptr, adj, vals, col_order, n, out_col,
-                out_vals);
+    SB_LAUNCH((permute_short_rows_kernel<I, N, V, 5>), grid, kSrBlock, 0, st,
+              (const RowRec<N> *)rec, (const N *)out_row_ptr, adj, vals, col_order, n, out_col,
+              out_vals);
     return;
   }
-  GatherLoader<I, N, V> ld{rec, adj, vals, col_order};
+  static const int stream_env = [] {
+    const char *e = getenv("SB200_P2D_STREAM");  // tuning: 0 = never, 1 = always
+    return e ? atoi(e) : -1;
+  }();
+  const bool local = row_order == nullptr || 2 * h_stats[1] >= (unsigned long long)n;
+  const bool stream = stream_env >= 0 ? stream_env != 0 : !local;
+  GatherLoader<I, N, V> ld{rec, adj, vals, col_order, stream};
   segmented_sort<I, N, V>(ws, ld, (const N *)out_row_ptr, n, m, nnz, out_col, out_vals);
 }
 

@@ -32,6 +32,7 @@ const DeviceInfo &device_info(int device) {
     SB_CUDA(cudaGetDeviceProperties(&p, device));
     infos[device].sm_count = p.multiProcessorCount;
     infos[device].max_smem_optin = (int)p.sharedMemPerBlockOptin;
+    infos[device].l2_bytes = (int64_t)p.l2CacheSize;
     // keep freed scratch blocks in the pool instead of returning them to the driver
     cudaMemPool_t pool;
     SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));

@@ -212,8 +212,10 @@ __global__ void __launch_bounds__(kSsBlock)
     int rank = 0;  // entries before q count when <=, entries after q when < (stable)
     for (int j = sb; j < q; j++) rank += s.key[j] <= k ? 1 : 0;
     for (int j = q + 1; j < sb + len; j++) rank += s.key[j] < k ? 1 : 0;
-    out_idx[first + sb + rank] = k;
-    if constexpr (has_val<V>) out_val[first + sb + rank] = s.val[q];
+    // outputs are written once and never read here: streaming stores keep them from pushing
+    // the renumbering table out of L2
+    st_stream(out_idx + first + sb + rank, k);
+    if constexpr (has_val<V>) st_stream(out_val + first + sb + rank, (V)s.val[q]);
   }
 
   // ---- mid segments: one warp each, normalized bitonic network in shared memory ----
@@ -253,8 +255,8 @@ __global__ void __launch_bounds__(kSsBlock)
       }
     }
     for (int x = lane; x < len; x += 32) {
-      out_idx[first + sb + x] = key[x];
-      if constexpr (has_val<V>) out_val[first + sb + x] = reinterpret_cast<V *>(s.val)[sb + x];
+      st_stream(out_idx + first + sb + x, key[x]);
+      if constexpr (has_val<V>) st_stream(out_val + first + sb + x, reinterpret_cast<V *>(s.val)[sb + x]);
     }
   }
 }

@@ -21,6 +21,8 @@ an oracle-backed stand-in for ``ops``; tests/test_sharded_gpu.py on 2 GPUs with 
 ``ops`` is an explicit parameter only so that the host logic can be exercised without a GPU;
 the product path never runs without the CUDA library.
 """
+import os
+import time
 from dataclasses import dataclass
 from typing import Optional
 
@@ -29,6 +31,29 @@ import torch.distributed as dist
 
 
 # ------------------------------------------------------------------------------- plumbing
+class _Trace:
+    """SB200_SHARD_TRACE=1: per-stage wall time (device synchronised) printed by rank 0."""
+    on = os.environ.get("SB200_SHARD_TRACE", "0") == "1"
+
+    def __init__(self, op):
+        self.op, self.t, self.rows = op, None, []
+        if self.on:
+            torch.cuda.synchronize()
+            self.t = time.perf_counter()
+
+    def mark(self, stage):
+        if self.on:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.rows.append((stage, (now - self.t) * 1e3))
+            self.t = now
+
+    def done(self):
+        if self.on and _world()[0] == 0:
+            print(f"[shard-trace] {self.op}: " +
+                  "  ".join(f"{k}={v:.3f}ms" for k, v in self.rows), flush=True)
+
+
 def _world(group=None):
     if not dist.is_available() or not dist.is_initialized():
         return 0, 1
@@ -138,14 +163,16 @@ def shard_csr(ops, n, m, row_ptr, col, vals, rank, world):
 
 
 # ------------------------------------------------------------------------------- COO -> CSR
-def coo_to_csr(ops, n, m, bounds, row, col, vals, group=None, nnz_dtype=torch.int32):
+def coo_to_csr(ops, n, m, bounds, row, col, vals, group=None, nnz_dtype=torch.int32, copy=True):
     """`row/col/vals` are this rank's entries: all nonzeros of rows [bounds[rank], bounds[rank+1])
     in any order.  COO-constructor sort + histogram/scan/copy run locally; one 8-byte
-    all_gather assembles the global offsets."""
+    all_gather assembles the global offsets.  With ``copy=False`` the caller's arrays are sorted
+    in place, as the reference's COO constructor does (format/coo.cc:110-157)."""
     rank, world = _world(group)
     lo, hi = bounds[rank], bounds[rank + 1]
-    row, col = row.clone(), col.clone()
-    vals = None if vals is None else vals.clone()
+    if copy:
+        row, col = row.clone(), col.clone()
+        vals = None if vals is None else vals.clone()
     ops.coo_sort_(n, m, row, col, vals)                      # format::COO constructor
     row_ptr, ocol, ovals = ops.coo_to_csr_block(lo, hi - lo, m, row, col, vals,
                                                 nnz_dtype=nnz_dtype)
@@ -175,7 +202,9 @@ def degree_reorder(ops, s: ShardedCSR, ascending=True, group=None, id_dtype=torc
     lo, hi = s.block(rank)
     nl = hi - lo
     dev = s.row_ptr.device
+    tr = _Trace("degree_reorder")
     local = ops.degree_reorder(nl, s.row_ptr, True, id_dtype=id_dtype)  # (deg asc, id desc)
+    tr.mark("local")
     maxdeg = int(_all_gather_i64(ops.max_degree(nl, s.row_ptr), dev, group).max())
     nbins = maxdeg + 1
     hist = ops.degree_histogram(nl, s.row_ptr, nbins)                   # int64[nbins]
@@ -185,6 +214,7 @@ def degree_reorder(ops, s: ShardedCSR, ascending=True, group=None, id_dtype=torc
         allh = allh.view(world, nbins)
     else:
         allh = hist.view(1, nbins)
+    tr.mark("hist_gather")
     # O(world * maxdeg) bookkeeping on the histograms (tiny next to n):
     total = allh.sum(0)
     g_start = torch.cumsum(total, 0) - total          # vertices with a smaller degree, anywhere
@@ -193,8 +223,12 @@ def degree_reorder(ops, s: ShardedCSR, ascending=True, group=None, id_dtype=torc
     offset = (g_start + later - l_start).contiguous()
     part = ops.degree_rank_combine(nl, s.row_ptr, local, offset,
                                    -1 if ascending else s.n - 1)
+    tr.mark("combine")
     counts = [s.bounds[r + 1] - s.bounds[r] for r in range(world)]
-    return _all_gather_var(part, counts, group)
+    out = _all_gather_var(part, counts, group)
+    tr.mark("allgather_perm")
+    tr.done()
+    return out
 
 
 # ------------------------------------------------------------------------------- Permute2D
@@ -213,17 +247,20 @@ def permute2d(ops, s: ShardedCSR, row_order, col_order, group=None):
     dev = s.col.device
     idt = s.col.dtype
     # ---- nnz-balanced blocks of the NEW row space (needs every row's degree once)
+    tr = _Trace("permute2d")
     deg_local = ops.degrees(nl, s.row_ptr, id_dtype=s.row_ptr.dtype)
     counts = [s.bounds[r + 1] - s.bounds[r] for r in range(world)]
     deg = _all_gather_var(deg_local, counts, group)
     new_deg = ops.permute1d(deg, row_order) if row_order is not None else deg
     new_ptr = ops.exclusive_scan(new_deg)
     nb = ops.partition_rows(s.n, s.nnz, new_ptr, world) if world > 1 else [0, s.n]
+    tr.mark("balance")
     # ---- sender
     my_new = row_order[lo:hi].contiguous() if row_order is not None else \
         torch.arange(lo, hi, dtype=idt, device=dev)
     local_rank = ops.rank_keys(my_new, s.n)                        # order my rows by new id
     p_ptr, p_col, p_val = ops.permute2d(nl, s.m, s.row_ptr, s.col, s.vals, local_rank, col_order)
+    tr.mark("local_permute")
     sorted_new = ops.permute1d(my_new, local_rank)                 # ascending new ids
     p_len = (p_ptr[1:] - p_ptr[:-1]).contiguous()
     cut = torch.searchsorted(sorted_new, torch.tensor(nb, dtype=idt, device=dev)).cpu().tolist()
@@ -232,17 +269,21 @@ def permute2d(ops, s: ShardedCSR, row_order, col_order, group=None):
     send_nnz = [ptr_at[q + 1] - ptr_at[q] for q in range(world)]
     recv_rows = _exchange_counts(send_rows, dev, group)
     recv_nnz = _exchange_counts(send_nnz, dev, group)
+    tr.mark("cuts_counts")
     # ---- exchange
     r_new = _all_to_all_var(sorted_new, send_rows, recv_rows, group)
     r_len = _all_to_all_var(p_len, send_rows, recv_rows, group)
     r_col = _all_to_all_var(p_col, send_nnz, recv_nnz, group)
     r_val = None if p_val is None else _all_to_all_var(p_val, send_nnz, recv_nnz, group)
+    tr.mark("all_to_all")
     # ---- receiver
     nlo, nhi = nb[rank], nb[rank + 1]
     r_ptr = ops.exclusive_scan(r_len)
     order = (r_new - nlo).to(idt)
     o_ptr, o_col, o_val = ops.permute2d(nhi - nlo, s.m, r_ptr, r_col, r_val, order, None)
     base = int(new_ptr[nlo])
+    tr.mark("place")
+    tr.done()
     return ShardedCSR(s.n, s.m, s.nnz, list(nb), o_ptr, o_col, o_val, base)
 
 
@@ -259,14 +300,18 @@ def csr_to_csc(ops, s: ShardedCSR, group=None):
     rank, world = _world(group)
     lo, hi = s.block(rank)
     dev = s.col.device
+    tr = _Trace("csr_to_csc")
     cp, rows, vals = ops.csr_to_csc_block(lo, hi - lo, s.m, s.row_ptr, s.col, s.vals)
+    tr.mark("local_csc")
     cnt = (cp[1:] - cp[:-1]).to(torch.int64)
     tot = cnt.clone()
     if world > 1:
         dist.all_reduce(tot, group=group)
+    tr.mark("allreduce_counts")
     gptr = ops.exclusive_scan(tot)                                   # int64[m+1], replicated
     cb = ops.partition_rows(s.m, s.nnz, gptr, world) if world > 1 else [0, s.m]
     at = cp[torch.tensor(cb, device=dev)].cpu().tolist()
+    tr.mark("scan_partition")
     send_cols = [cb[q + 1] - cb[q] for q in range(world)]
     send_nnz = [at[q + 1] - at[q] for q in range(world)]
     clo, chi = cb[rank], cb[rank + 1]
@@ -276,12 +321,17 @@ def csr_to_csc(ops, s: ShardedCSR, group=None):
     r_cnt = _all_to_all_var(cnt.to(s.row_ptr.dtype), send_cols, recv_cols, group)
     r_row = _all_to_all_var(rows, send_nnz, recv_nnz, group)
     r_val = None if vals is None else _all_to_all_var(vals, send_nnz, recv_nnz, group)
+    tr.mark("all_to_all")
     if world == 1:
         return ShardedCSC(s.n, s.m, s.nnz, list(cb), cp, rows, vals, 0)
     # segments arrive ordered (source, column); the result needs (column, source)
     seg_ptr = ops.exclusive_scan(r_cnt)
     k = torch.arange(world * ncl, dtype=s.col.dtype, device=dev)
     order = ((k % ncl) * world + k // ncl).to(s.col.dtype)           # (s, c) -> c * world + s
+    tr.mark("order")
     o_ptr, o_row, o_val = ops.permute2d(world * ncl, s.n, seg_ptr, r_row, r_val, order, None)
+    tr.mark("interleave")
     col_ptr = o_ptr[::world].contiguous()
+    tr.mark("col_ptr")
+    tr.done()
     return ShardedCSC(s.n, s.m, s.nnz, list(cb), col_ptr, o_row, o_val, int(gptr[clo]))
