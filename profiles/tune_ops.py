@@ -22,6 +22,10 @@ args = ap.parse_args()
 dev = torch.device("cuda", 0)
 if args.graph == "poisson":
     n, rp, col, vals = synth.poisson2d(args.size, args.size, device=dev)
+elif args.graph == "band":
+    n, row, col = synth.band(1 << args.size, 31, 0.5, seed=45, shuffle_seed=46, device=dev)
+    rp = synth.csr_from_sorted_coo(n, row)
+    vals = synth.hash_vals(col.numel(), device=dev)
 elif args.graph == "er":
     n, row, col = synth.erdos_renyi(1 << args.size, 8, device=dev)
     rp = synth.csr_from_sorted_coo(n, row)

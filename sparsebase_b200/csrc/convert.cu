@@ -28,12 +28,14 @@ namespace sb200 {
 constexpr int kBfBlock = 256;
 constexpr int kBfIpt = 4;
 
-// A run of more than kGapMax empty segments (isolated vertices, or the columns a row block of
+// A run of kGapMax or more empty segments (isolated vertices, or the columns a row block of
 // a sharded matrix never touches) is not filled by the one thread that sees the boundary: it
 // is appended to a list and filled afterwards by gap_fill_kernel with the whole grid.  (One
 // thread filling 8.4 M trailing entries cost 30 ms in the row-block CSR->CSC.)
-constexpr int kGapMax = 32;
-constexpr int kGapWarpMax = 8192;  // longer gaps are filled by all CTAs together
+constexpr int kGapMax = 1024;        // shorter runs are filled in place (a power-law matrix has
+                                     // millions of short runs: deferring them all through one
+                                     // list counter cost 26 ms on R-MAT-26)
+constexpr int kGapWarpMax = 32768;   // longer gaps are filled by all CTAs together
 struct GapRec {
   int64_t lo, hi;  // ptr[lo..hi] = value
   int64_t value;

@@ -23,27 +23,82 @@ inline unsigned map_grid(int64_t n, int per_thread = 1) {
 }
 
 // ---------------------------------------------------------------- degree features
+// Four consecutive rows per thread: the five row_ptr entries they need are one 16-byte load
+// (when the array is 16-byte aligned) plus the first entry of the next thread, which comes by
+// shuffle; the four results leave as one 16-byte streaming store (4-byte outputs).
+constexpr int kDfPer = 4;
+
+template <typename N>
+__device__ __forceinline__ void df_load5(const N *__restrict__ row_ptr, int64_t n, int64_t i0,
+                                         N (&p)[kDfPer + 1]) {
+  const bool vec = sizeof(N) == 4 && i0 + kDfPer <= n &&
+                   (reinterpret_cast<uintptr_t>(row_ptr) & 15) == 0;
+  if (vec) {
+    const uint4 q = *reinterpret_cast<const uint4 *>(row_ptr + i0);
+    p[0] = (N)q.x;
+    p[1] = (N)q.y;
+    p[2] = (N)q.z;
+    p[3] = (N)q.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kDfPer; k++) p[k] = i0 + k <= n ? row_ptr[i0 + k] : N(0);
+  }
+  // entry i0 + 4 = the next thread's first entry (lane 31 and the ragged end read it)
+  const N nxt = __shfl_down_sync(0xffffffffu, p[0], 1);
+  p[kDfPer] = nxt;
+  if (lane_id() == 31 || i0 + 2 * kDfPer > n) p[kDfPer] = i0 + kDfPer <= n ? row_ptr[i0 + kDfPer] : N(0);
+}
+
+template <typename T>
+__device__ __forceinline__ void df_store4(T *__restrict__ out, int64_t n, int64_t i0,
+                                          const T (&v)[kDfPer]) {
+  if (sizeof(T) == 4 && i0 + kDfPer <= n && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    uint4 q;
+    q.x = *reinterpret_cast<const unsigned *>(&v[0]);
+    q.y = *reinterpret_cast<const unsigned *>(&v[1]);
+    q.z = *reinterpret_cast<const unsigned *>(&v[2]);
+    q.w = *reinterpret_cast<const unsigned *>(&v[3]);
+    __stcs(reinterpret_cast<uint4 *>(out + i0), q);
+  } else {
+#pragma unroll
+    for (int k = 0; k < kDfPer; k++)
+      if (i0 + k < n) st_stream(out + i0 + k, v[k]);
+  }
+}
+
 template <typename I, typename N>
-__global__ void degrees_kernel(const N *__restrict__ row_ptr, int64_t n, I *__restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) st_stream(out + i, (I)(row_ptr[i + 1] - row_ptr[i]));
+__global__ void __launch_bounds__(kMapBlock)
+    degrees_kernel(const N *__restrict__ row_ptr, int64_t n, I *__restrict__ out) {
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kDfPer;
+  N p[kDfPer + 1];
+  df_load5<N>(row_ptr, n, i0 < n ? i0 : n, p);  // whole warps take part in the shuffle
+  if (i0 >= n) return;
+  I v[kDfPer];
+#pragma unroll
+  for (int k = 0; k < kDfPer; k++) v[k] = (I)(p[k + 1] - p[k]);
+  df_store4<I>(out, n, i0, v);
 }
 
 // dist[i] = (rows[i+1]-rows[i]) / (FeatureType)num_edges  -- the N-typed difference is
 // converted to F and divided with IEEE round-to-nearest (no fast-math in this library).
 template <typename N, typename F>
-__global__ void degree_distribution_kernel(const N *__restrict__ row_ptr, int64_t n, N num_edges,
-                                           F *__restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const N d = row_ptr[i + 1] - row_ptr[i];
-    F q;
+__global__ void __launch_bounds__(kMapBlock)
+    degree_distribution_kernel(const N *__restrict__ row_ptr, int64_t n, N num_edges,
+                               F *__restrict__ out) {
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kDfPer;
+  N p[kDfPer + 1];
+  df_load5<N>(row_ptr, n, i0 < n ? i0 : n, p);
+  if (i0 >= n) return;
+  F v[kDfPer];
+#pragma unroll
+  for (int k = 0; k < kDfPer; k++) {
+    const N d = p[k + 1] - p[k];
     if constexpr (std::is_same_v<F, float>)
-      q = __fdiv_rn((float)d, (float)num_edges);
+      v[k] = __fdiv_rn((float)d, (float)num_edges);
     else
-      q = __ddiv_rn((double)d, (double)num_edges);
-    st_stream(out + i, q);
+      v[k] = __ddiv_rn((double)d, (double)num_edges);
   }
+  df_store4<F>(out, n, i0, v);
 }
 
 // ---------------------------------------------------------------- permutations
@@ -585,7 +640,7 @@ int sb200_degrees(int device, int64_t n, const void *row_ptr, void *out_degrees,
     dispatch_inv(id_type, nnz_type, SB200_VOID, false, [&](auto I_, auto N_, auto) {
       using I = decltype(I_);
       using N = decltype(N_);
-      SB_LAUNCH((degrees_kernel<I, N>), map_grid(n), kMapBlock, 0, (cudaStream_t)stream,
+      SB_LAUNCH((degrees_kernel<I, N>), map_grid(n, kDfPer), kMapBlock, 0, (cudaStream_t)stream,
                 (const N *)row_ptr, n, (I *)out_degrees);
     });
   });
@@ -603,7 +658,7 @@ int sb200_degree_distribution(int device, int64_t n, int64_t nnz, const void *ro
     auto run = [&](auto N_, auto F_) {
       using N = decltype(N_);
       using F = decltype(F_);
-      SB_LAUNCH((degree_distribution_kernel<N, F>), map_grid(n), kMapBlock, 0, st,
+      SB_LAUNCH((degree_distribution_kernel<N, F>), map_grid(n, kDfPer), kMapBlock, 0, st,
                 (const N *)row_ptr, n, (N)nnz, (F *)out_dist);
     };
     if (dtype_size(nnz_type) == 4) {
