@@ -569,7 +569,7 @@ void rs_launch_downsweep_pipe_off(cudaStream_t st, RsBufs<K, V1, V2> src, RsBufs
                                   const RsChunking &ch, int shift, int bits,
                                   const int64_t *spine) {
   constexpr int smem = (int)sizeof(RsPipeSmem<BLOCK, IPT, K, V1, V2, Off>);
-  constexpr int MINB = (smem <= 112 * 1024 && BLOCK <= 512) ? 2 : 1;
+  constexpr int MINB = (smem <= 112 * 1024 && BLOCK <= 512 && IPT <= 8) ? 2 : 1;
   auto kern = rs_downsweep_pipe_kernel<BLOCK, IPT, MINB, K, V1, V2, Off>;
   SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   SB_LAUNCH(kern, ch.nchunks, BLOCK, smem, st, (const K *)src.k, dst.k, (const V1 *)src.v1,
@@ -586,6 +586,20 @@ void rs_launch_downsweep_pipe(cudaStream_t st, RsBufs<K, V1, V2> src, RsBufs<K, 
                                                                  spine);
 }
 
+// Default shape of the pipelined downsweep: 512 threads, ONE CTA per SM with the full register
+// file, and the largest tile whose two stage buffers fit the 227 KB of shared memory -- 8192
+// records (16 per thread) for records of up to 12 bytes.  Per tile and bin a CTA writes a run of
+// tile/256 records; doubling the tile from 4096 doubled the runs to 128 bytes and took 30 % off
+// the pass (CSR->CSC on C2 3.6 -> 2.6 ms, on C3 11.4 -> 7.9 ms) although half as many warps are
+// resident.
+template <typename K, typename V1, typename V2>
+constexpr int rs_auto_ipt() {
+  constexpr int rec = (int)sizeof(K) + (has_val<V1> ? (int)sizeof(V1) : 0) +
+                      (has_val<V2> ? (int)sizeof(V2) : 0);
+  constexpr int budget = 212 * 1024;  // stage buffers; counters, offsets and barriers on top
+  return 2 * 512 * 16 * rec <= budget ? 16 : (2 * 512 * 12 * rec <= budget ? 12 : 8);
+}
+
 template <typename K, typename V1, typename V2>
 inline bool rs_bulk_aligned(const RsBufs<K, V1, V2> &b) {
   uintptr_t a = reinterpret_cast<uintptr_t>(b.k);
@@ -594,9 +608,9 @@ inline bool rs_bulk_aligned(const RsBufs<K, V1, V2> &b) {
   return (a & 15) == 0;
 }
 
-// Downsweep configuration.  Default (0): bulk-copy pipelined kernel, 512 threads x 8 records
-// (4096-record tile, two CTAs per SM).  SB200_RS_CONFIG = 10..14 select the register-prefetch
-// kernel in the shapes kept for tuning runs; it is also the route for unaligned inputs.
+// Downsweep configuration.  Default (0): bulk-copy pipelined kernel in the shape chosen by
+// rs_auto_ipt.  SB200_RS_CONFIG = 1..5 are other shapes of it, 10..14 the register-prefetch
+// kernel (also the route for unaligned inputs), all kept for tuning runs.
 inline int rs_config() {
   static const int cfg = [] {
     const char *e = getenv("SB200_RS_CONFIG");
@@ -607,12 +621,14 @@ inline int rs_config() {
 inline int rs_chunks_per_sm() {
   static const int v = [] {
     const char *e = getenv("SB200_RS_CHUNKS_PER_SM");
-    const int x = e ? atoi(e) : 4;
-    return x > 0 ? x : 4;
+    const int x = e ? atoi(e) : 2;
+    return x > 0 ? x : 2;
   }();
   return v;
 }
-inline int rs_config_tile(int cfg) {
+template <typename K, typename V1, typename V2>
+inline int rs_config_tile(int cfg, bool bulk) {
+  if (cfg == 0) return bulk ? 512 * rs_auto_ipt<K, V1, V2>() : 512 * 8;
   switch (cfg) {
     case 11: return 256 * 12;
     case 12: return 512 * 12;
@@ -620,6 +636,9 @@ inline int rs_config_tile(int cfg) {
     case 14: return 256 * 16;
     case 1: return 256 * 16;
     case 2: return 512 * 6;
+    case 3: return 512 * 16;
+    case 4: return 1024 * 8;
+    case 5: return 512 * 8;
     default: return 512 * 8;
   }
 }
@@ -643,9 +662,12 @@ void radix_sort(Workspace &ws, RsBufs<K, V1, V2> in, RsBufs<K, V1, V2> out,
   }
   const DeviceInfo &di = device_info(ws.device());
   const int cfg = rs_config();
+  // the bulk-copy kernel needs 16-byte aligned inputs in every pass: `in` for the first one,
+  // then out / tmp alternately
+  const bool bulk = rs_bulk_aligned(in) && rs_bulk_aligned(out) && (P < 2 || rs_bulk_aligned(tmp));
   RsChunking ch;
   ch.n = n;
-  ch.tile = rs_config_tile(cfg);
+  ch.tile = rs_config_tile<K, V1, V2>(cfg, bulk);
   ch.tiles = ceil_div(n, ch.tile);
   int64_t max_chunks = (int64_t)di.sm_count * rs_chunks_per_sm();
   ch.nchunks = (int)(ch.tiles < max_chunks ? ch.tiles : max_chunks);
@@ -665,7 +687,6 @@ void radix_sort(Workspace &ws, RsBufs<K, V1, V2> in, RsBufs<K, V1, V2> out,
                 bits, spine_in);
       exclusive_scan<int64_t>(ws, LoadFn<int64_t>{spine_in}, spine,
                               (int64_t)(1 << bits) * ch.nchunks);
-      const bool bulk = rs_bulk_aligned(src);
       if (cfg == 11)
         rs_launch_downsweep<256, 12, 2, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
       else if (cfg == 12)
@@ -678,8 +699,15 @@ void radix_sort(Workspace &ws, RsBufs<K, V1, V2> in, RsBufs<K, V1, V2> out,
         rs_launch_downsweep_pipe<256, 16, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
       else if (cfg == 2 && bulk)
         rs_launch_downsweep_pipe<512, 6, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
-      else if (cfg == 0 && bulk)
+      else if (cfg == 3 && bulk)
+        rs_launch_downsweep_pipe<512, 16, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
+      else if (cfg == 4 && bulk)
+        rs_launch_downsweep_pipe<1024, 8, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
+      else if (cfg == 5 && bulk)
         rs_launch_downsweep_pipe<512, 8, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
+      else if (cfg == 0 && bulk)
+        rs_launch_downsweep_pipe<512, rs_auto_ipt<K, V1, V2>(), K, V1, V2>(st, src, dst, ch, shift,
+                                                                         bits, spine);
       else
         rs_launch_downsweep<512, 8, 2, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
       src = dst;
