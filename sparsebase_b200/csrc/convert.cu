@@ -570,7 +570,8 @@ void expand_ptr(Workspace &ws, const N *ptr, int64_t n_seg, int64_t nnz, const I
 // =====================================================================================
 template <typename I, typename N, typename V>
 void to_csc_core(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const I *row, const I *col,
-                 const V *vals, N *out_col_ptr, I *out_row, V *out_vals) {
+                 const V *vals, N *out_col_ptr, I *out_row, V *out_vals,
+                 bool rows_ascending = false) {
   // n = number of col_ptr segments: dims[0] for the reference layout (square assumption),
   // m for the row-block variant used by the multi-GPU path
   using UI = typename std::make_unsigned<I>::type;
@@ -600,9 +601,12 @@ void to_csc_core(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const I *row,
                               {k_out, (UI *)out_row, nullptr}, {k_tmp, r_tmp, nullptr}, nnz,
                               ranges);
   }
-  // col_ptr from the sorted column keys; the secondary stream (rows) gives the CSC-ctor check
-  build_ptr_and_copy<I, N, NoVal>(ws, (const I *)k_out, (const I *)out_row, nullptr, nnz, n,
-                                  out_col_ptr, nullptr, nullptr, h_flags);
+  // col_ptr from the sorted column keys; the secondary stream (rows) gives the CSC-ctor check.
+  // When the row stream was non-decreasing (row ids expanded from a row_ptr), a stable sort by
+  // column leaves the rows of every column ascending by construction: nothing to check.
+  build_ptr_and_copy<I, N, NoVal>(ws, (const I *)k_out,
+                                  rows_ascending ? (const I *)nullptr : (const I *)out_row,
+                                  nullptr, nnz, n, out_col_ptr, nullptr, nullptr, h_flags);
   if (h_flags[1]) {  // csc.cc:99-157: some column has unsorted rows -> sort every column
     if constexpr (has_val<V>)
       compressed_sort_inplace<I, N, V>(ws, out_col_ptr, out_row, out_vals, n, n, nnz);
@@ -738,7 +742,7 @@ int sb200_csr_to_csc(int device, int64_t n, int64_t m, int64_t nnz, const void *
       expand_ptr<I, N, NoVal>(ws, (const N *)row_ptr, n, nnz, (const I *)nullptr,
                               (const NoVal *)nullptr, rows, (I *)nullptr, (NoVal *)nullptr);
       to_csc_core<I, N, V>(ws, n, m, nnz, rows, (const I *)col, (const V *)vals,
-                           (N *)out_col_ptr, (I *)out_row, (V *)out_vals);
+                           (N *)out_col_ptr, (I *)out_row, (V *)out_vals, true);
     });
   });
 }
@@ -794,7 +798,7 @@ int sb200_csr_to_csc_block(int device, int64_t row_lo, int64_t n_local, int64_t 
                               (I)row_lo);
       // col_ptr gets m+1 entries here (one per global column)
       to_csc_core<I, N, V>(ws, m, m, nnz, rows, (const I *)col, (const V *)vals,
-                           (N *)out_col_ptr, (I *)out_row, (V *)out_vals);
+                           (N *)out_col_ptr, (I *)out_row, (V *)out_vals, true);
     });
   });
 }

@@ -35,11 +35,23 @@ __device__ __forceinline__ unsigned rs_digit(K key, int shift, unsigned mask) {
   return (unsigned)(key >> shift) & mask;
 }
 
+// Segmented mode (radix_sort_segmented): the array is a concatenation of independent segments,
+// every chunk is ONE tile-sized piece of one segment, and the spine is laid out
+// [segment][bin][chunk of the segment], so that a flat exclusive scan of it yields
+// (segment start) + (records of the segment with a smaller digit) + (same digit, earlier chunk).
+struct RsSeg {
+  int64_t begin;       // first record of the chunk
+  int64_t spine_base;  // spine slot of (bin 0, this chunk)
+  int count;           // records in the chunk (<= tile)
+  int stride;          // chunks in this chunk's segment = spine distance between bins
+};
+
 struct RsChunking {
   int64_t n;
   int64_t tiles;  // in units of `tile` records (the downsweep tile of the chosen configuration)
   int nchunks;
   int tile;
+  const RsSeg *seg = nullptr;  // non-null: segmented mode
   __host__ __device__ int64_t tile_begin(int c) const { return tiles * c / nchunks; }
   __host__ __device__ int64_t tile_end(int c) const { return tiles * (c + 1) / nchunks; }
 };
@@ -59,10 +71,17 @@ __global__ void __launch_bounds__(kRsBlock)
   for (int i = threadIdx.x; i < kRsWarps * kRsMaxBins; i += kRsBlock) (&hist[0][0])[i] = 0;
   __syncthreads();
   const int c = blockIdx.x;
-  const int64_t begin = ch.tile_begin(c) * ch.tile;
+  int64_t begin = ch.tile_begin(c) * ch.tile;
   int64_t end = ch.tile_end(c) * ch.tile;
   if (end > ch.n) end = ch.n;
-  const bool aligned = (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
+  bool aligned = (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
+  RsSeg sg = {};
+  if (ch.seg) {
+    sg = ch.seg[c];
+    begin = sg.begin;
+    end = begin + sg.count;
+    aligned = false;  // chunk starts are arbitrary
+  }
   int64_t base = begin;
   if (aligned) {
     const int64_t step = (int64_t)kRsBlock * kVec * 4;
@@ -94,12 +113,15 @@ __global__ void __launch_bounds__(kRsBlock)
     }
   }
   __syncthreads();
-  const int nbins = 1 << bits;
+  const int nbins = ch.seg ? kRsMaxBins : 1 << bits;  // segmented spine: fixed 256 bins
   for (int d = threadIdx.x; d < nbins; d += kRsBlock) {
     unsigned s = 0;
 #pragma unroll
     for (int w = 0; w < kRsWarps; w++) s += hist[w][d];
-    spine[(int64_t)d * ch.nchunks + c] = s;
+    if (ch.seg)
+      spine[sg.spine_base + (int64_t)d * sg.stride] = s;
+    else
+      spine[(int64_t)d * ch.nchunks + c] = s;
   }
 }
 
@@ -338,7 +360,8 @@ struct RsPipeSmem {
   __align__(8) uint64_t bar[2];
 };
 
-template <int BLOCK, int IPT, int MINB, typename K, typename V1, typename V2, typename Off>
+template <int BLOCK, int IPT, int MINB, bool SEG, typename K, typename V1, typename V2,
+          typename Off>
 __global__ void __launch_bounds__(BLOCK, MINB)
     rs_downsweep_pipe_kernel(const K *__restrict__ kin, K *__restrict__ kout,
                              const V1 *__restrict__ v1in, V1 *__restrict__ v1out,
@@ -357,7 +380,10 @@ __global__ void __launch_bounds__(BLOCK, MINB)
   const int nbins = 1 << bits;
   const int c = blockIdx.x;
   const int64_t n = ch.n;
-  const int64_t t_begin = ch.tile_begin(c), t_end = ch.tile_end(c);
+  RsSeg sg = {};
+  if (SEG) sg = ch.seg[c];
+  // segmented mode: the chunk is one (possibly short, arbitrarily aligned) tile
+  const int64_t t_begin = SEG ? 0 : ch.tile_begin(c), t_end = SEG ? 1 : ch.tile_end(c);
   if (t_begin >= t_end) return;
 
   auto issue = [&](int64_t tile, int st) {  // one thread
@@ -369,7 +395,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     if constexpr (has_val<V2>)
       rs_bulk_g2s(s.s2[st], v2in + base, (unsigned)(kTile * sizeof(V2)), &s.bar[st]);
   };
-  auto full = [&](int64_t tile) { return (tile + 1) * kTile <= n; };
+  auto full = [&](int64_t tile) { return !SEG && (tile + 1) * kTile <= n; };
 
   if (threadIdx.x == 0) {
     rs_mbar_init(&s.bar[0], 1);
@@ -380,20 +406,22 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     if (t_begin + 1 < t_end && full(t_begin + 1)) issue(t_begin + 1, 1);
   }
   if ((int)threadIdx.x < nbins)
-    s.bin_off[threadIdx.x] = spine[(int64_t)threadIdx.x * ch.nchunks + c];
+    s.bin_off[threadIdx.x] = SEG ? spine[sg.spine_base + (int64_t)threadIdx.x * sg.stride]
+                                    : spine[(int64_t)threadIdx.x * ch.nchunks + c];
   __syncthreads();  // barriers initialised before anybody waits on them
 
   unsigned phase0 = 0, phase1 = 0;
   for (int64_t tile = t_begin; tile < t_end; tile++) {
     const int st = (int)((tile - t_begin) & 1);
-    const int64_t tile_base_idx = tile * kTile;
-    const int tile_count = full(tile) ? kTile : (int)(n - tile_base_idx);
+    const int64_t tile_base_idx = SEG ? sg.begin : tile * kTile;
+    const int tile_count = SEG ? sg.count : (full(tile) ? kTile : (int)(n - tile_base_idx));
+    const bool bulk_tile = full(tile);
     const int local_base = (int)wid * (IPT * 32) + (int)lane;
     K *const sk = s.sk[st];
     [[maybe_unused]] typename Smem::P1 *const s1 = s.s1[st];
     [[maybe_unused]] typename Smem::P2 *const s2 = s.s2[st];
 
-    if (tile_count == kTile) {
+    if (bulk_tile) {
       if (st == 0) {
         rs_mbar_wait(&s.bar[0], phase0);
         phase0 ^= 1u;
@@ -406,7 +434,8 @@ __global__ void __launch_bounds__(BLOCK, MINB)
       // all-ones keys.  Padding has the largest digit and comes last in the tile, so it ranks
       // behind every real record (slots >= tile_count, never written) and only inflates the
       // count of the last bin of the last tile, which nobody reads any more.
-      for (int q = threadIdx.x; q < kTile; q += BLOCK) {
+      const int pad_end = SEG ? (tile_count + 31) & ~31 : kTile;  // SEG: later rounds are skipped
+      for (int q = threadIdx.x; q < pad_end; q += BLOCK) {
         if (q < tile_count) {
           sk[q] = ld_stream(kin + tile_base_idx + q);
           if constexpr (has_val<V1>) s1[q] = ld_stream(v1in + tile_base_idx + q);
@@ -421,12 +450,17 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     K key[IPT];
     [[maybe_unused]] typename Smem::P1 p1[IPT];
     [[maybe_unused]] typename Smem::P2 p2[IPT];
+    // rounds of this warp that hold records (all of them except in a short segmented chunk,
+    // where whole warps have nothing to rank)
+    const int warp_first = (int)wid * (IPT * 32);
 #pragma unroll
     for (int r = 0; r < IPT; r++) {
       const int q = local_base + r * 32;
-      key[r] = sk[q];
-      if constexpr (has_val<V1>) p1[r] = s1[q];
-      if constexpr (has_val<V2>) p2[r] = s2[q];
+      if (!SEG || warp_first + r * 32 < tile_count) {
+        key[r] = sk[q];
+        if constexpr (has_val<V1>) p1[r] = s1[q];
+        if constexpr (has_val<V2>) p2[r] = s2[q];
+      }
     }
     {
       unsigned *z = reinterpret_cast<unsigned *>(&s.cnt[0][0]);
@@ -436,7 +470,9 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     // ---- 1a. all the matches of the tile, back to back ----
     unsigned peers[IPT];
 #pragma unroll
-    for (int r = 0; r < IPT; r++) peers[r] = rs_match_digit(rs_digit(key[r], shift, mask));
+    for (int r = 0; r < IPT; r++)
+      if (!SEG || warp_first + r * 32 < tile_count)
+        peers[r] = rs_match_digit(rs_digit(key[r], shift, mask));
     __syncthreads();  // stage buffer is in registers everywhere; counters are zero
 
     // ---- 1b. stable ranking inside the warp (rounds in order, lanes in order) ----
@@ -444,6 +480,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     unsigned lp[IPT];  // (rank inside the warp << 8) | digit
 #pragma unroll
     for (int r = 0; r < IPT; r++) {
+      if (SEG && warp_first + r * 32 >= tile_count) break;
       const unsigned d = rs_digit(key[r], shift, mask);
       const int leader = __ffs(peers[r]) - 1;
       unsigned base = 0;
@@ -479,6 +516,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     // ---- 3. lay the tile out in digit order in the (now free) stage buffer ----
 #pragma unroll
     for (int r = 0; r < IPT; r++) {
+      if (SEG && warp_first + r * 32 >= tile_count) break;
       const unsigned d = lp[r] & 0xffu;
       const unsigned at = (lp[r] >> 8) + my_cnt[d] + s.excl[d];
       sk[at] = key[r];
@@ -564,25 +602,26 @@ void rs_launch_downsweep(cudaStream_t st, RsBufs<K, V1, V2> src, RsBufs<K, V1, V
 // One launch of the bulk-copy pipelined downsweep (inputs must be 16-byte aligned).  Records
 // narrow enough for two resident CTAs per SM are compiled for 64 registers; wider ones (one
 // CTA per SM by shared memory anyway) get the full register file.
-template <int BLOCK, int IPT, typename K, typename V1, typename V2, typename Off>
+template <int BLOCK, int IPT, bool SEG, typename K, typename V1, typename V2, typename Off>
 void rs_launch_downsweep_pipe_off(cudaStream_t st, RsBufs<K, V1, V2> src, RsBufs<K, V1, V2> dst,
                                   const RsChunking &ch, int shift, int bits,
                                   const int64_t *spine) {
   constexpr int smem = (int)sizeof(RsPipeSmem<BLOCK, IPT, K, V1, V2, Off>);
   constexpr int MINB = (smem <= 112 * 1024 && BLOCK <= 512 && IPT <= 8) ? 2 : 1;
-  auto kern = rs_downsweep_pipe_kernel<BLOCK, IPT, MINB, K, V1, V2, Off>;
+  SB_REQUIRE(SEG == (ch.seg != nullptr), SB200_ERR_BAD_ARG, "segmented-mode mismatch");
+  auto kern = rs_downsweep_pipe_kernel<BLOCK, IPT, MINB, SEG, K, V1, V2, Off>;
   SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   SB_LAUNCH(kern, ch.nchunks, BLOCK, smem, st, (const K *)src.k, dst.k, (const V1 *)src.v1,
             dst.v1, (const V2 *)src.v2, dst.v2, ch, shift, bits, spine);
 }
-template <int BLOCK, int IPT, typename K, typename V1, typename V2>
+template <int BLOCK, int IPT, typename K, typename V1, typename V2, bool SEG = false>
 void rs_launch_downsweep_pipe(cudaStream_t st, RsBufs<K, V1, V2> src, RsBufs<K, V1, V2> dst,
                               const RsChunking &ch, int shift, int bits, const int64_t *spine) {
   if (ch.n < (1ll << 31))
-    rs_launch_downsweep_pipe_off<BLOCK, IPT, K, V1, V2, int32_t>(st, src, dst, ch, shift, bits,
+    rs_launch_downsweep_pipe_off<BLOCK, IPT, SEG, K, V1, V2, int32_t>(st, src, dst, ch, shift, bits,
                                                                  spine);
   else
-    rs_launch_downsweep_pipe_off<BLOCK, IPT, K, V1, V2, int64_t>(st, src, dst, ch, shift, bits,
+    rs_launch_downsweep_pipe_off<BLOCK, IPT, SEG, K, V1, V2, int64_t>(st, src, dst, ch, shift, bits,
                                                                  spine);
 }
 
@@ -640,6 +679,53 @@ inline int rs_config_tile(int cfg, bool bulk) {
     case 4: return 1024 * 8;
     case 5: return 512 * 8;
     default: return 512 * 8;
+  }
+}
+
+// Stable sort of every segment of a concatenation of segments by the key bits [0, key_bits):
+// `seg` holds `nchunks` tile-sized chunk descriptors (device memory, tile = rs_seg_tile<...>()),
+// built by the caller.  Same buffer convention as radix_sort.  Records never leave their segment.
+template <typename K, typename V1, typename V2>
+constexpr int rs_seg_tile() {
+  // smaller than the default tile: most segments are not much longer than the caller's
+  // threshold, and a chunk ranks whole 32-record rounds (two CTAs per SM here)
+  return 512 * 8;
+}
+template <typename K, typename V1, typename V2>
+void radix_sort_segmented(Workspace &ws, RsBufs<K, V1, V2> in, RsBufs<K, V1, V2> out,
+                          RsBufs<K, V1, V2> tmp, int64_t n, const RsSeg *seg, int64_t nchunks,
+                          int key_bits) {
+  if (n <= 0 || nchunks <= 0) return;
+  cudaStream_t st = ws.stream();
+  const int P = (key_bits + kRsMaxBits - 1) / kRsMaxBits;
+  if (P == 0) {
+    SB_CUDA(cudaMemcpyAsync(out.k, in.k, n * sizeof(K), cudaMemcpyDeviceToDevice, st));
+    if constexpr (has_val<V1>)
+      SB_CUDA(cudaMemcpyAsync(out.v1, in.v1, n * sizeof(V1), cudaMemcpyDeviceToDevice, st));
+    if constexpr (has_val<V2>)
+      SB_CUDA(cudaMemcpyAsync(out.v2, in.v2, n * sizeof(V2), cudaMemcpyDeviceToDevice, st));
+    return;
+  }
+  RsChunking ch;
+  ch.n = n;
+  ch.tile = rs_seg_tile<K, V1, V2>();
+  ch.tiles = nchunks;
+  ch.nchunks = (int)nchunks;
+  ch.seg = seg;
+  const int64_t spine_len = (int64_t)kRsMaxBins * nchunks;
+  int64_t *spine_in = ws.alloc<int64_t>(spine_len + 1);
+  int64_t *spine = ws.alloc<int64_t>(spine_len + 1);
+  RsBufs<K, V1, V2> src = in;
+  int shift = 0;
+  for (int pass = 0; pass < P; pass++) {
+    const int bits = (key_bits - shift + (P - pass) - 1) / (P - pass);
+    RsBufs<K, V1, V2> dst = ((P - 1 - pass) % 2 == 0) ? out : tmp;
+    SB_LAUNCH((rs_upsweep_kernel<K>), ch.nchunks, kRsBlock, 0, st, (const K *)src.k, ch, shift,
+              bits, spine_in);
+    exclusive_scan<int64_t>(ws, LoadFn<int64_t>{spine_in}, spine, spine_len);
+    rs_launch_downsweep_pipe<512, 8, K, V1, V2, true>(st, src, dst, ch, shift, bits, spine);
+    src = dst;
+    shift += bits;
   }
 }
 

@@ -398,6 +398,13 @@ __device__ long long cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a
       if (k < pcount) {
         if (m[u] == s.pkey[pbase + k]) {
           const unsigned dg = (unsigned)(xe[u] - xs[u]);
+          // the winner is expanded in the next level, after two cluster barriers and the
+          // ordering: pull its adjacency into L2 meanwhile (the lists are read once per
+          // traversal, so the expansion would otherwise wait for HBM)
+          if (dg > 0) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + xs[u]));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + xe[u] - 1));
+          }
           s.px[pbase + k] = (int64_t)xs[u];
           s.pd[pbase + k] = dg;
           mymax = dg > mymax ? dg : mymax;

@@ -262,6 +262,12 @@ __global__ void __launch_bounds__(kSsBlock)
 }
 
 // ------------------------------------------------------------------ long segments
+// Segments longer than kSsLong are sorted by a SEGMENTED radix sort on the index alone
+// (radix_sort_segmented): the entries of the long segments are concatenated, every segment is
+// cut into tile-sized chunks, and each LSD pass ranks a record inside its own segment.  Cost:
+// ceil(bits(n_idx) / 8) passes over (index, value) records -- the composite (segment rank,
+// index) key of the first version needed 5-7 passes over wider records and was 55 % of
+// Permute2D on R-MAT-25.
 template <typename N>
 struct LongLenFn {
   const int64_t *list;
@@ -271,44 +277,90 @@ struct LongLenFn {
     return (int64_t)ptr[r + 1] - (int64_t)ptr[r];
   }
 };
+template <typename N>
+struct LongChunksFn {  // number of tile-sized chunks of long segment k
+  const int64_t *list;
+  const N *ptr;
+  int tile;
+  __device__ int64_t operator()(int64_t k) const {
+    int64_t r = list[k];
+    return ((int64_t)ptr[r + 1] - (int64_t)ptr[r] + tile - 1) / tile;
+  }
+};
 
+// One thread per chunk: which long segment it belongs to, and where its records / spine slots are.
+static __global__ void ss_long_chunks_kernel(const int64_t *__restrict__ offs,
+                                      const int64_t *__restrict__ chunk_first, int64_t nlong,
+                                      int64_t nchunks, int tile, RsSeg *__restrict__ seg,
+                                      int *__restrict__ chunk_seg) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  int64_t lo = 0, hi = nlong;  // last k with chunk_first[k] <= c
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (chunk_first[mid] <= c)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  const int64_t local = c - chunk_first[lo];
+  const int64_t len = offs[lo + 1] - offs[lo];
+  const int64_t rest = len - local * tile;
+  RsSeg g;
+  g.begin = offs[lo] + local * tile;
+  g.count = (int)(rest < tile ? rest : tile);
+  g.stride = (int)(chunk_first[lo + 1] - chunk_first[lo]);
+  g.spine_base = chunk_first[lo] * kRsMaxBins + local;
+  seg[c] = g;
+  chunk_seg[c] = (int)lo;
+}
+
+// One CTA per chunk: pull the chunk's entries through the loader (coalesced inside the source
+// row, renumbering gathers batched) into the concatenated arrays.
 template <typename I, typename N, typename V, typename Loader>
-__global__ void ss_long_fill_kernel(Loader ld, const N *__restrict__ ptr,
-                                    const int64_t *__restrict__ list,
-                                    const int64_t *__restrict__ offs, int64_t nlong,
-                                    int64_t total, int idx_bits, uint64_t *__restrict__ keys,
-                                    V *__restrict__ vals) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    int64_t lo = 0, hi = nlong;  // last k with offs[k] <= e
-    while (hi - lo > 1) {
-      int64_t mid = (lo + hi) >> 1;
-      if (offs[mid] <= e)
-        lo = mid;
-      else
-        hi = mid;
+__global__ void __launch_bounds__(256)
+    ss_long_fill_kernel(Loader ld, const int64_t *__restrict__ list,
+                        const int64_t *__restrict__ offs, const RsSeg *__restrict__ seg,
+                        const int *__restrict__ chunk_seg,
+                        typename std::make_unsigned<I>::type *__restrict__ keys,
+                        V *__restrict__ vals) {
+  using UI = typename std::make_unsigned<I>::type;
+  const RsSeg g = seg[blockIdx.x];
+  const int k = chunk_seg[blockIdx.x];
+  const int64_t src0 = ld.seg_base(list[k]) + (g.begin - offs[k]);
+  constexpr int kBatch = 4;
+  for (int q0 = 0; q0 < g.count; q0 += 256 * kBatch) {
+    I raw[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int q = q0 + u * 256 + (int)threadIdx.x;
+      if (q < g.count) {
+        raw[u] = ld.raw_key(src0 + q);
+        if constexpr (has_val<V>) vals[g.begin + q] = ld.val(src0 + q);
+      }
     }
-    const int64_t r = list[lo];
-    const int64_t p = ld.seg_base(r) + (e - offs[lo]);
-    keys[e] = ((uint64_t)lo << idx_bits) | (uint64_t)ld.map_key(ld.raw_key(p));
-    if constexpr (has_val<V>) vals[e] = ld.val(p);
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int q = q0 + u * 256 + (int)threadIdx.x;
+      if (q < g.count) keys[g.begin + q] = (UI)ld.map_key(raw[u]);
+    }
   }
 }
 
 template <typename I, typename N, typename V>
-__global__ void ss_long_store_kernel(const N *__restrict__ ptr, const int64_t *__restrict__ list,
-                                     const int64_t *__restrict__ offs, int64_t total,
-                                     int idx_bits, const uint64_t *__restrict__ keys,
-                                     const V *__restrict__ vals, I *__restrict__ out_idx,
-                                     V *__restrict__ out_val) {
-  const uint64_t mask = (1ull << idx_bits) - 1ull;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    const uint64_t k = keys[e];
-    const int64_t lo = (int64_t)(k >> idx_bits);
-    const int64_t dst = (int64_t)ptr[list[lo]] + (e - offs[lo]);
-    out_idx[dst] = (I)(k & mask);
-    if constexpr (has_val<V>) out_val[dst] = vals[e];
+__global__ void __launch_bounds__(256)
+    ss_long_store_kernel(const N *__restrict__ ptr, const int64_t *__restrict__ list,
+                         const int64_t *__restrict__ offs, const RsSeg *__restrict__ seg,
+                         const int *__restrict__ chunk_seg,
+                         const typename std::make_unsigned<I>::type *__restrict__ keys,
+                         const V *__restrict__ vals, I *__restrict__ out_idx,
+                         V *__restrict__ out_val) {
+  const RsSeg g = seg[blockIdx.x];
+  const int k = chunk_seg[blockIdx.x];
+  const int64_t dst0 = (int64_t)ptr[list[k]] + (g.begin - offs[k]);
+  for (int q = threadIdx.x; q < g.count; q += 256) {
+    st_stream(out_idx + dst0 + q, (I)ld_stream(keys + g.begin + q));
+    if constexpr (has_val<V>) st_stream(out_val + dst0 + q, ld_stream(vals + g.begin + q));
   }
 }
 
@@ -338,32 +390,43 @@ void segmented_sort(Workspace &ws, Loader ld, const N *ptr, int64_t n_seg, int64
   SB_CUDA(cudaStreamSynchronize(st));
   if (nlong == 0) return;
 
-  // ---- long segments: composite-key global radix sort ----
+  // ---- long segments: segmented radix sort on the index ----
+  using UI = typename std::make_unsigned<I>::type;
+  constexpr int kTileL = rs_seg_tile<UI, V, NoVal>();
   int64_t *offs = ws.alloc<int64_t>((int64_t)nlong + 1);
+  int64_t *chunk_first = ws.alloc<int64_t>((int64_t)nlong + 1);
   exclusive_scan<int64_t>(ws, LongLenFn<N>{long_list, ptr}, offs, (int64_t)nlong);
-  int64_t total = 0;
+  exclusive_scan<int64_t>(ws, LongChunksFn<N>{long_list, ptr, kTileL}, chunk_first,
+                          (int64_t)nlong);
+  int64_t total = 0, nchunks = 0;
   SB_CUDA(cudaMemcpyAsync(&total, offs + nlong, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(&nchunks, chunk_first + nlong, sizeof(int64_t), cudaMemcpyDeviceToHost,
+                          st));
   SB_CUDA(cudaStreamSynchronize(st));
+  SB_REQUIRE(nchunks < (1ll << 31), SB200_ERR_BAD_ARG, "too many long-segment chunks");
   const int idx_bits = bits_for((uint64_t)(n_idx > 0 ? n_idx - 1 : 0));
-  const int rank_bits = bits_for((uint64_t)nlong - 1);
-  SB_REQUIRE(idx_bits + rank_bits <= 64, SB200_ERR_BAD_ARG,
-             "long-segment key does not fit 64 bits (%d + %d)", idx_bits, rank_bits);
-  uint64_t *kin = ws.alloc<uint64_t>(total), *ka = ws.alloc<uint64_t>(total),
-           *kb = ws.alloc<uint64_t>(total);
+  const int P = (idx_bits + kRsMaxBits - 1) / kRsMaxBits;
+  RsSeg *seg = ws.alloc<RsSeg>(nchunks);
+  int *chunk_seg = ws.alloc<int>(nchunks);
+  SB_LAUNCH(ss_long_chunks_kernel, (unsigned)ceil_div(nchunks, 256), 256, 0, st,
+            (const int64_t *)offs, (const int64_t *)chunk_first, (int64_t)nlong, nchunks, kTileL,
+            seg, chunk_seg);
+  UI *kin = ws.alloc<UI>(total), *ka = ws.alloc<UI>(total);
+  UI *kb = P > 1 ? ws.alloc<UI>(total) : nullptr;
   V *vin = nullptr, *va = nullptr, *vb = nullptr;
   if constexpr (has_val<V>) {
     vin = ws.alloc<V>(total);
     va = ws.alloc<V>(total);
-    vb = ws.alloc<V>(total);
+    vb = P > 1 ? ws.alloc<V>(total) : nullptr;
   }
-  const int grid = device_info(ws.device()).sm_count * 8;
-  SB_LAUNCH((ss_long_fill_kernel<I, N, V, Loader>), grid, 256, 0, st, ld, ptr, long_list, offs,
-            (int64_t)nlong, total, idx_bits, kin, vin);
-  std::vector<RsBitRange> ranges = {{0, idx_bits}, {idx_bits, idx_bits + rank_bits}};
-  radix_sort<uint64_t, V, NoVal>(ws, {kin, vin, nullptr}, {ka, va, nullptr}, {kb, vb, nullptr},
-                                 total, ranges);
-  SB_LAUNCH((ss_long_store_kernel<I, N, V>), grid, 256, 0, st, ptr, long_list, offs, total,
-            idx_bits, (const uint64_t *)ka, (const V *)va, out_idx, out_val);
+  SB_LAUNCH((ss_long_fill_kernel<I, N, V, Loader>), (unsigned)nchunks, 256, 0, st, ld,
+            (const int64_t *)long_list, (const int64_t *)offs, (const RsSeg *)seg,
+            (const int *)chunk_seg, kin, vin);
+  radix_sort_segmented<UI, V, NoVal>(ws, {kin, vin, nullptr}, {ka, va, nullptr},
+                                     {kb, vb, nullptr}, total, seg, nchunks, idx_bits);
+  SB_LAUNCH((ss_long_store_kernel<I, N, V>), (unsigned)nchunks, 256, 0, st, ptr,
+            (const int64_t *)long_list, (const int64_t *)offs, (const RsSeg *)seg,
+            (const int *)chunk_seg, (const UI *)ka, (const V *)va, out_idx, out_val);
 }
 
 }  // namespace sb200

@@ -206,3 +206,35 @@ def test_degree_features_vector_edges(sb, orc, n):
         if len(col):
             assert eq(host(sb.degree_distribution(n, len(col), dev(rp), torch.float32)),
                       orc.degree_distribution(n, rp, col, z))
+
+
+@pytest.mark.parametrize("types", [(np.int32, np.int32, np.float32), (np.int64, np.int64, np.float64),
+                                   (np.int32, np.int32, None)],
+                         ids=["i32_i32_f32", "i64_i64_f64", "i32_i32_void"])
+def test_long_rows_segmented_sort(sb, orc, types):
+    """Rows longer than the on-chip limit go through the segmented radix sort; rows longer than
+    its 8192-record tile span several chunks (lengths around the chunk size on purpose)."""
+    idt, nt, vt = types
+    rng = np.random.default_rng(41)
+    n = 30011
+    lens = {0: 20000, 5: 9000, 6: 8192, 7: 8193, 11: 1025, 12: 1024, 29999: 16385}
+    rows = [np.full(c, r) for r, c in lens.items()] + [rng.integers(13, n - 20, 50000)]
+    cols = [rng.choice(n, c, replace=False) for c in lens.values()] + [rng.integers(0, n, 50000)]
+    key = np.unique(np.concatenate(rows).astype(np.int64) * n + np.concatenate(cols))
+    row, col = (key // n).astype(idt), (key % n).astype(idt)
+    rp = graphs.csr_of(n, row, col, nt)
+    vals = None if vt is None else graphs.vals_for(len(col), dtype=vt)
+    order = rng.permutation(n).astype(idt)
+    exp = orc.permute2d(n, n, rp, col, vals, order, order)
+    got = sb.permute2d(n, n, dev(rp), dev(col), dev(vals), dev(order), dev(order))
+    for a, b, what in zip(got, exp, ("row_ptr", "col", "vals")):
+        assert eq(host(a), b), f"permute2d long rows {what}"
+    # CSR constructor sort of the same rows after shuffling every row
+    sh = col.copy()
+    for r in lens:
+        a, b = int(rp[r]), int(rp[r + 1])
+        sh[a:b] = rng.permutation(sh[a:b])
+    ecol, evals = orc.csr_ctor_sort(n, n, rp, sh, vals)
+    dcol, dvals = dev(sh), dev(vals)
+    sb.compressed_sort_(n, n, dev(rp), dcol, dvals)
+    assert eq(host(dcol), ecol) and eq(host(dvals), evals)
