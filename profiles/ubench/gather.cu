@@ -21,6 +21,9 @@ __device__ __forceinline__ unsigned gload(const unsigned *p, uint64_t pol) {
   return v;
 }
 // each thread: 4 x (stream-read idx+val, gather table[idx], stream-write)
+// ROWS: the two input streams are read as randomly placed 16-element rows (a row gather)
+// instead of sequentially.
+__device__ bool g_rows = false;
 template <int MODE>
 __global__ void k(const unsigned *__restrict__ idx, const unsigned *__restrict__ val,
                   const unsigned *__restrict__ table, unsigned *__restrict__ o1,
@@ -30,7 +33,14 @@ __global__ void k(const unsigned *__restrict__ idx, const unsigned *__restrict__
   int64_t i0 = ((int64_t)blockIdx.x * blockDim.x) * 4 + threadIdx.x;
   unsigned a[4], b[4];
 #pragma unroll
-  for (int u = 0; u < 4; u++) { int64_t i = i0 + u * blockDim.x; if (i < n) { a[u] = __ldcs(idx + i); b[u] = __ldcs(val + i); } }
+  for (int u = 0; u < 4; u++) {
+    int64_t i = i0 + u * blockDim.x;
+    if (i < n) {
+      int64_t p = i;
+      if (g_rows) p = (int64_t)(((uint64_t)hash32((unsigned)(i >> 4) * 0x9e3779b9u) * (uint64_t)(n >> 4)) >> 32) * 16 + (i & 15);
+      a[u] = __ldcs(idx + p); b[u] = __ldcs(val + p);
+    }
+  }
 #pragma unroll
   for (int u = 0; u < 4; u++) { int64_t i = i0 + u * blockDim.x; if (i < n) a[u] = gload<MODE>(table + a[u], pol); }
 #pragma unroll
@@ -60,7 +70,7 @@ int main() {
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   printf("persisting L2 limit %zu, max %d, l2 %d\n", lim, p.persistingL2CacheMaxSize, p.l2CacheSize);
   for (int pass = 0; pass < 2; pass++) {
-    if (pass == 1) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)p.persistingL2CacheMaxSize); printf("-- persisting limit set to max --\n"); }
+    if (pass == 1) { bool t = true; cudaMemcpyToSymbol(g_rows, &t, sizeof(bool)); printf("-- input streams read as random 64-byte rows --\n"); }
     for (int mb : {16, 32, 64, 128, 256}) {
       unsigned tsize = (unsigned)((int64_t)mb << 18);
       fill_idx<<<(unsigned)((n + 255) / 256), 256>>>(idx, n, tsize, 7u);
