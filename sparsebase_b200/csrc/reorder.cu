@@ -533,14 +533,25 @@ __global__ void __launch_bounds__(kSrBlock, MINB)
       const unsigned len_o = __shfl_sync(0xffffffffu, len, owner);
       if (sidx < total) {
         const I k = c[u];
-        unsigned rank = 0;
+        // unique column ids (every valid input): the rank is the number of smaller ids.  The
+        // loop also counts the ids <= k; more than one means duplicates, which take the
+        // reference's (col, val) order in the rare path below.
+        unsigned lt = 0, le = 0;
 #pragma unroll
         for (int t = 0; t < kShortRow; t++) {
           if ((unsigned)t < len_o) {
             const I kj = sk[ex_o + t];
+            lt += kj < k ? 1u : 0u;
+            le += kj <= k ? 1u : 0u;
+          }
+        }
+        unsigned rank = lt;
+        if (le - lt > 1u) {  // duplicate column ids: (col, val) order, then position (csr.cc:147)
+          rank = 0;
+          for (unsigned jj = ex_o; jj < ex_o + len_o; jj++) {
+            const I kj = sk[jj];
             bool before = kj < k;
-            if (kj == k) {  // duplicate column ids: (col, val) order, then position (csr.cc:147)
-              const unsigned jj = ex_o + t;
+            if (kj == k) {
               if constexpr (has_val<V>) {
                 const V vj = sv[jj];
                 before = vj < cv[u] || (!(cv[u] < vj) && jj < sidx);
@@ -553,6 +564,133 @@ __global__ void __launch_bounds__(kSrBlock, MINB)
         }
         st_stream(out_col + ob0 + ex_o + rank, k);
         if constexpr (has_val<V>) st_stream(out_vals + ob0 + ex_o + rank, (V)cv[u]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- matrices whose longest row has <= 64 entries (random graphs of moderate degree, banded
+//      matrices).  Same warp-owned scheme as the short-row kernel, without block barriers and
+//      without the window bookkeeping of ss_tile_kernel: one warp owns R consecutive NEW rows
+//      (R = 16 for rows <= 32, R = 8 for rows <= 64, so a batch has <= 512 entries), fetches
+//      their entries in concatenated order four 32-slot rounds at a time (row gathers, then the
+//      dependent col_order gathers, then the staging stores), ranks every entry inside its row
+//      by enumeration in the warp's shared-memory slice and writes the batch as one contiguous
+//      run.  ncu on C3 had ss_tile_kernel at 7 ms where a barrier-free gather of the same
+//      access mix (profiles/ubench/gather.cu) takes 1.6 ms. ----
+constexpr int kMrCap = 512;
+// warps per CTA so that the static shared memory stays under 48 KB for 8-byte ids / values
+template <typename I, typename V>
+constexpr int mr_block() {
+  return (sizeof(I) + (has_val<V> ? sizeof(V) : 0)) <= 8 ? 256 : 128;
+}
+
+template <typename I, typename N, typename V, int R>
+__global__ void __launch_bounds__((mr_block<I, V>()))
+    permute_mid_rows_kernel(const RowRec<N> *__restrict__ rec, const N *__restrict__ out_ptr,
+                            const I *__restrict__ adj, const V *__restrict__ vals,
+                            const I *__restrict__ col_order, int64_t n, bool stream,
+                            I *__restrict__ out_col, V *__restrict__ out_vals) {
+  using VR = typename std::conditional<has_val<V>, V, char>::type;
+  constexpr int kMrBlock = mr_block<I, V>();
+  __shared__ I stage_k[kMrBlock / 32][kMrCap];
+  __shared__ VR stage_v[kMrBlock / 32][has_val<V> ? kMrCap : 1];
+  __shared__ unsigned char stage_own[kMrBlock / 32][kMrCap];
+  const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
+  I *sk = stage_k[wid];
+  [[maybe_unused]] VR *sv = stage_v[wid];
+  unsigned char *own = stage_own[wid];
+  const int64_t nbatches = (n + R - 1) / R;
+  const int64_t wstride = ((int64_t)gridDim.x * kMrBlock) >> 5;
+  for (int64_t bt = (((int64_t)blockIdx.x * kMrBlock) >> 5) + wid; bt < nbatches; bt += wstride) {
+    const int64_t j = bt * R + lane;
+    N ob = 0, p = 0;
+    unsigned len = 0;
+    if (lane < (unsigned)R && j < n) {
+      const RowRec<N> rr = rec[j];
+      ob = out_ptr[j];
+      len = (unsigned)rr.len;
+      p = rr.base;
+    }
+    const N ob0 = __shfl_sync(0xffffffffu, ob, 0);
+    const unsigned incl = warp_inclusive_scan(len);
+    const unsigned excl = incl - len;
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);  // <= R * (512 / R)
+    for (unsigned u = 0; u < len; u++) own[excl + u] = (unsigned char)lane;
+    __syncwarp();
+    // ---- fetch, four rounds in flight ----
+    for (unsigned base = 0; base < total; base += 128) {
+      I c[4];
+      [[maybe_unused]] VR cv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const unsigned sidx = base + u * 32 + lane;
+        const unsigned owner = sidx < total ? own[sidx] : 0u;
+        const N p_o = __shfl_sync(0xffffffffu, p, owner);
+        const unsigned ex_o = __shfl_sync(0xffffffffu, excl, owner);
+        if (sidx < total) {
+          const N src = p_o + (N)(sidx - ex_o);
+          c[u] = stream ? __ldcs(adj + src) : __ldg(adj + src);
+          if constexpr (has_val<V>) cv[u] = stream ? __ldcs(vals + src) : __ldg(vals + src);
+        }
+      }
+      if (col_order) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (base + u * 32 + lane < total) c[u] = __ldg(col_order + c[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const unsigned sidx = base + u * 32 + lane;
+        if (sidx < total) {
+          sk[sidx] = c[u];
+          if constexpr (has_val<V>) sv[sidx] = cv[u];
+        }
+      }
+    }
+    __syncwarp();
+    // ---- rank inside the row, write to the sorted place ----
+    for (unsigned base = 0; base < total; base += 32) {
+      const unsigned sidx = base + lane;
+      const unsigned owner = sidx < total ? own[sidx] : 0u;
+      const unsigned ex_o = __shfl_sync(0xffffffffu, excl, owner);
+      const unsigned len_o = __shfl_sync(0xffffffffu, len, owner);
+      if (sidx < total) {
+        const I k = sk[sidx];
+        unsigned lt = 0, le = 0;  // see permute_short_rows_kernel
+        const I *rowk = sk + ex_o;
+        unsigned t = 0;
+        for (; t + 4 <= len_o; t += 4) {
+          const I k0 = rowk[t], k1 = rowk[t + 1], k2 = rowk[t + 2], k3 = rowk[t + 3];
+          lt += (k0 < k ? 1u : 0u) + (k1 < k ? 1u : 0u) + (k2 < k ? 1u : 0u) + (k3 < k ? 1u : 0u);
+          le += (k0 <= k ? 1u : 0u) + (k1 <= k ? 1u : 0u) + (k2 <= k ? 1u : 0u) +
+                (k3 <= k ? 1u : 0u);
+        }
+        for (; t < len_o; t++) {
+          const I kj = rowk[t];
+          lt += kj < k ? 1u : 0u;
+          le += kj <= k ? 1u : 0u;
+        }
+        unsigned rank = lt;
+        if (le - lt > 1u) {  // duplicate column ids: (col, val) order, then position (csr.cc:147)
+          rank = 0;
+          for (unsigned jj = ex_o; jj < ex_o + len_o; jj++) {
+            const I kj = sk[jj];
+            bool before = kj < k;
+            if (kj == k) {
+              if constexpr (has_val<V>) {
+                const V vj = sv[jj], vm = sv[sidx];
+                before = vj < vm || (!(vm < vj) && jj < sidx);
+              } else {
+                before = jj < sidx;
+              }
+            }
+            rank += before ? 1u : 0u;
+          }
+        }
+        st_stream(out_col + ob0 + ex_o + rank, k);
+        if constexpr (has_val<V>) st_stream(out_vals + ob0 + ex_o + rank, (V)sv[sidx]);
       }
     }
     __syncwarp();
@@ -590,12 +728,31 @@ void permute2d_impl(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const N *x
               out_vals);
     return;
   }
+  static const int mid_env = [] {
+    const char *e = getenv("SB200_P2D_MID");  // tuning: 0 disables the mid-row kernel
+    return e ? atoi(e) : 1;
+  }();
   static const int stream_env = [] {
     const char *e = getenv("SB200_P2D_STREAM");  // tuning: 0 = never, 1 = always
     return e ? atoi(e) : -1;
   }();
   const bool local = row_order == nullptr || 2 * h_stats[1] >= (unsigned long long)n;
   const bool stream = stream_env >= 0 ? stream_env != 0 : !local;
+  if (h_max <= 64ull && mid_env) {
+    constexpr int kMrBlock = mr_block<I, V>();
+    if (h_max <= 32ull) {
+      const unsigned grid = (unsigned)ceil_div(ceil_div(n, 16), kMrBlock / 32);
+      SB_LAUNCH((permute_mid_rows_kernel<I, N, V, 16>), grid, kMrBlock, 0, st,
+                (const RowRec<N> *)rec, (const N *)out_row_ptr, adj, vals, col_order, n, stream,
+                out_col, out_vals);
+    } else {
+      const unsigned grid = (unsigned)ceil_div(ceil_div(n, 8), kMrBlock / 32);
+      SB_LAUNCH((permute_mid_rows_kernel<I, N, V, 8>), grid, kMrBlock, 0, st,
+                (const RowRec<N> *)rec, (const N *)out_row_ptr, adj, vals, col_order, n, stream,
+                out_col, out_vals);
+    }
+    return;
+  }
   GatherLoader<I, N, V> ld{rec, adj, vals, col_order, stream};
   segmented_sort<I, N, V>(ws, ld, (const N *)out_row_ptr, n, m, nnz, out_col, out_vals);
 }

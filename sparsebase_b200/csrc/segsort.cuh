@@ -210,7 +210,9 @@ __global__ void __launch_bounds__(kSsBlock)
     if (len > kSsEnum) continue;
     const I k = s.key[q];
     int rank = 0;  // entries before q count when <=, entries after q when < (stable)
+#pragma unroll 4
     for (int j = sb; j < q; j++) rank += s.key[j] <= k ? 1 : 0;
+#pragma unroll 4
     for (int j = q + 1; j < sb + len; j++) rank += s.key[j] < k ? 1 : 0;
     // outputs are written once and never read here: streaming stores keep them from pushing
     // the renumbering table out of L2

@@ -238,3 +238,48 @@ def test_long_rows_segmented_sort(sb, orc, types):
     dcol, dvals = dev(sh), dev(vals)
     sb.compressed_sort_(n, n, dev(rp), dcol, dvals)
     assert eq(host(dcol), ecol) and eq(host(dvals), evals)
+
+
+@pytest.mark.parametrize("maxdeg", [9, 32, 33, 64])
+@pytest.mark.parametrize("types", [(np.int32, np.int32, np.float32), (np.int32, np.int64, np.float32),
+                                   (np.int64, np.int64, np.float64), (np.int32, np.int32, None)],
+                         ids=["i32_i32_f32", "i32_i64_f32", "i64_i64_f64", "i32_i32_void"])
+def test_permute2d_mid_rows_kernel(sb, orc, types, maxdeg):
+    """Longest row in 9..64: the barrier-free warp-batch kernel (16 rows per warp up to 32
+    entries, 8 rows per warp up to 64), with empty rows, a ragged last batch, rows of exactly
+    the maximum length, and row / column orders that differ."""
+    idt, nt, vt = types
+    rng = np.random.default_rng(1000 + maxdeg)
+    n = 20011
+    deg = rng.integers(0, maxdeg + 1, size=n)
+    deg[rng.integers(0, n, size=300)] = 0
+    deg[[0, 17, n - 1]] = maxdeg
+    row = np.repeat(np.arange(n), deg)
+    col = np.concatenate([rng.choice(n, size=d, replace=False) for d in deg]).astype(np.int64)
+    rp = graphs.csr_of(n, row.astype(idt), col.astype(idt), nt)
+    cc = col.astype(idt)
+    vv = None if vt is None else graphs.vals_for(len(cc), dtype=vt)
+    cc2, vv2 = orc.csr_ctor_sort(n, n, rp, cc, vv)
+    ro, co = rng.permutation(n).astype(idt), rng.permutation(n).astype(idt)
+    for r_, c_ in ((ro, ro), (ro, co), (None, co), (ro, None)):
+        exp = orc.permute2d(n, n, rp, cc2, vv2, r_, c_)
+        got = sb.permute2d(n, n, dev(rp), dev(cc2), dev(vv2), dev(r_), dev(c_))
+        for a, b, what in zip(got, exp, ("row_ptr", "col", "vals")):
+            assert eq(host(a), b), f"mid-row permute2d {what} {idt} {nt} {vt} max={maxdeg}"
+
+
+def test_mid_rows_duplicate_columns(sb, orc):
+    rng = np.random.default_rng(321)
+    n = 3001
+    deg = rng.integers(0, 41, size=n)
+    row = np.repeat(np.arange(n), deg).astype(np.int32)
+    col = np.concatenate([np.sort(rng.integers(0, 25, size=d) + rng.integers(0, n - 25))
+                          for d in deg]).astype(np.int32)
+    vals = rng.permutation(len(col)).astype(np.float32)
+    rp = graphs.csr_of(n, row, col)
+    cc, vv = orc.csr_ctor_sort(n, n, rp, col, vals)
+    order = rng.permutation(n).astype(np.int32)
+    exp = orc.permute2d(n, n, rp, cc, vv, order, order)
+    got = sb.permute2d(n, n, dev(rp), dev(cc), dev(vv), dev(order), dev(order))
+    for a, b, what in zip(got, exp, ("row_ptr", "col", "vals")):
+        assert eq(host(a), b), f"mid rows with duplicate columns: {what}"
