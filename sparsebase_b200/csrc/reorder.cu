@@ -723,9 +723,20 @@ void permute2d_impl(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const N *x
     // entries) are fetched from HBM once.  (A grid-stride loop over a capped grid spreads the
     // resident warps over distant row ranges and doubled the DRAM read traffic.)
     const unsigned grid = (unsigned)ceil_div(n, (int64_t)kSrBlock);
-    SB_LAUNCH((permute_short_rows_kernel<I, N, V, 5>), grid, kSrBlock, 0, st,
-              (const RowRec<N> *)rec, (const N *)out_row_ptr, adj, vals, col_order, n, out_col,
-              out_vals);
+    static const int minb = [] {
+      const char *e = getenv("SB200_SR_MINB");  // tuning: resident CTAs the kernel is compiled for
+      return e ? atoi(e) : 6;
+    }();
+    // wide ids / values do not fit 40 registers
+    constexpr bool narrow = sizeof(I) == 4 && sizeof(N) == 4 && (!has_val<V> || sizeof(V) == 4);
+    if (minb == 5 || !narrow)
+      SB_LAUNCH((permute_short_rows_kernel<I, N, V, 5>), grid, kSrBlock, 0, st,
+                (const RowRec<N> *)rec, (const N *)out_row_ptr, adj, vals, col_order, n, out_col,
+                out_vals);
+    else  // 40 registers: 48 resident warps per SM
+      SB_LAUNCH((permute_short_rows_kernel<I, N, V, (narrow ? 6 : 5)>), grid, kSrBlock, 0, st,
+                (const RowRec<N> *)rec, (const N *)out_row_ptr, adj, vals, col_order, n, out_col,
+                out_vals);
     return;
   }
   static const int mid_env = [] {
