@@ -21,6 +21,10 @@ args = ap.parse_args()
 dev = torch.device("cuda", 0)
 if args.graph == "poisson":
     n, rp, col, vals = synth.poisson2d(args.grid, args.grid, device=dev)
+elif args.graph == "rmat":  # --grid = scale
+    n, row, col = synth.rmat(args.grid, 8, device=dev)
+    rp = synth.csr_from_sorted_coo(n, row)
+    vals = synth.hash_vals(col.numel(), device=dev)
 else:  # er: --grid = log2(n)
     n, row, col = synth.erdos_renyi(1 << args.grid, 8, device=dev)
     rp = synth.csr_from_sorted_coo(n, row)
@@ -43,5 +47,19 @@ for _ in range(args.reps):
         lib.coo_to_csr(n, n, row, col, vals)
     if "degree_reorder" in ops:
         lib.degree_reorder(n, rp, True)
+    if "coo_sort" in ops:  # COO constructor on a shuffled edge list
+        sh = torch.randperm(nnz, generator=g, device=dev)
+        r2, c2, v2 = row[sh].contiguous(), col[sh].contiguous(), vals[sh].contiguous()
+        lib.coo_sort_(n, n, r2, c2, v2)
+    if "compressed_sort" in ops:  # CSR constructor on rows whose columns were renumbered
+        c3 = perm[col.to(torch.int64)].contiguous()
+        lib.compressed_sort_(n, n, rp, c3, vals.clone())
+    if "features" in ops:
+        lib.degrees(n, rp)
+        lib.degree_distribution(n, nnz, rp)
+        lib.permute1d(vals[:n].contiguous(), perm)
+        lib.inverse_permutation(perm)
+        lib.csr_to_coo(n, n, rp, col, vals)
+        lib.coo_to_csc(n, n, row, col, vals)
 torch.cuda.synchronize()
 print("done", n, nnz)

@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-for mb in 5 6; do SB200_SR_MINB=$mb python profiles/tune_ops.py --graph poisson --size 4096 --ops permute2d_rcm,permute2d_rand --reps 10 2>&1 | tail -1; done
+timeout 900 python profiles/bench_configs.py --config C5 --rcm --reps 2 --out gpurun_out/c37_C5.json > gpurun_out/c37_C5.log 2>&1; tail -c 300 gpurun_out/c37_C5.log

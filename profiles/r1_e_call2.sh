@@ -1,6 +1,6 @@
-set -x
 mkdir -p gpurun_out
-( time timeout 600 python -m pytest tests/test_sharded_gpu.py -x -q -m gpu ) > gpurun_out/m3_pytest.log 2>&1
-tail -3 gpurun_out/m3_pytest.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/m3_bench2.json 2> gpurun_out/m3_bench2.err
-tail -3 gpurun_out/m3_bench2.err
+timeout 900 ncu --set full --clock-control none --kernel-name-base demangled -k regex:"sb200::" -c 120 -f -o gpurun_out/f_ops python profiles/prof_driver.py --ops rcm,permute2d,coo_sort,compressed_sort,features --graph rmat --grid 21 --reps 1 > gpurun_out/f_ncu_ops.log 2>&1
+tail -2 gpurun_out/f_ncu_ops.log
+python profiles/ncu_summary.py gpurun_out/f_ops.ncu-rep > gpurun_out/f_ncu_full_ops_rmat.md 2> gpurun_out/f_err.log
+wc -l gpurun_out/f_ncu_full_ops_rmat.md
+rm -f gpurun_out/f_ops.ncu-rep
