@@ -648,8 +648,8 @@ inline bool rs_bulk_aligned(const RsBufs<K, V1, V2> &b) {
 }
 
 // Downsweep configuration.  Default (0): bulk-copy pipelined kernel in the shape chosen by
-// rs_auto_ipt.  SB200_RS_CONFIG = 1..5 are other shapes of it, 10..14 the register-prefetch
-// kernel (also the route for unaligned inputs), all kept for tuning runs.
+// rs_auto_ipt.  SB200_RS_CONFIG=5 is its 4096-record / two-CTA shape and 10 the
+// register-prefetch kernel (also the route for unaligned inputs); both kept for A/B runs.
 inline int rs_config() {
   static const int cfg = [] {
     const char *e = getenv("SB200_RS_CONFIG");
@@ -668,18 +668,7 @@ inline int rs_chunks_per_sm() {
 template <typename K, typename V1, typename V2>
 inline int rs_config_tile(int cfg, bool bulk) {
   if (cfg == 0) return bulk ? 512 * rs_auto_ipt<K, V1, V2>() : 512 * 8;
-  switch (cfg) {
-    case 11: return 256 * 12;
-    case 12: return 512 * 12;
-    case 13: return 384 * 10;
-    case 14: return 256 * 16;
-    case 1: return 256 * 16;
-    case 2: return 512 * 6;
-    case 3: return 512 * 16;
-    case 4: return 1024 * 8;
-    case 5: return 512 * 8;
-    default: return 512 * 8;
-  }
+  return 512 * 8;  // cfg 5 (pipelined, two CTAs per SM) and cfg 10 (register-prefetch kernel)
 }
 
 // Stable sort of every segment of a concatenation of segments by the key bits [0, key_bits):
@@ -773,23 +762,7 @@ void radix_sort(Workspace &ws, RsBufs<K, V1, V2> in, RsBufs<K, V1, V2> out,
                 bits, spine_in);
       exclusive_scan<int64_t>(ws, LoadFn<int64_t>{spine_in}, spine,
                               (int64_t)(1 << bits) * ch.nchunks);
-      if (cfg == 11)
-        rs_launch_downsweep<256, 12, 2, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
-      else if (cfg == 12)
-        rs_launch_downsweep<512, 12, 1, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
-      else if (cfg == 13)
-        rs_launch_downsweep<384, 10, 2, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
-      else if (cfg == 14)
-        rs_launch_downsweep<256, 16, 2, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
-      else if (cfg == 1 && bulk)
-        rs_launch_downsweep_pipe<256, 16, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
-      else if (cfg == 2 && bulk)
-        rs_launch_downsweep_pipe<512, 6, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
-      else if (cfg == 3 && bulk)
-        rs_launch_downsweep_pipe<512, 16, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
-      else if (cfg == 4 && bulk)
-        rs_launch_downsweep_pipe<1024, 8, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
-      else if (cfg == 5 && bulk)
+      if (cfg == 5 && bulk)
         rs_launch_downsweep_pipe<512, 8, K, V1, V2>(st, src, dst, ch, shift, bits, spine);
       else if (cfg == 0 && bulk)
         rs_launch_downsweep_pipe<512, rs_auto_ipt<K, V1, V2>(), K, V1, V2>(st, src, dst, ch, shift,
