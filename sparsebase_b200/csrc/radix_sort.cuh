@@ -11,10 +11,16 @@
 //   upsweep   : grid of `nchunks` CTAs, each histograms the current digit of its contiguous
 //               chunk of tiles in shared memory (warp-private counters) -> spine[bin][chunk]
 //   spine     : exclusive scan of the bin-major spine (decoupled look-back scan, scan.cuh)
-//   downsweep : same chunks; per 4096-key tile: warp-synchronous match_any ranking (stable),
-//               cross-warp digit scan, records staged through shared memory in digit order so
-//               that global writes are coalesced runs; running per-bin offsets stay in smem.
+//   downsweep : same chunks; per tile (8192 records by default): the tile arrives by bulk
+//               async copy (cp.async.bulk + mbarrier, two stage buffers), warp-synchronous
+//               stable ranking (ballot matching + warp-private counters), cross-warp digit scan,
+//               records laid out in digit order in the stage buffer so that global writes are
+//               coalesced runs; running per-bin offsets stay in smem
+//               (rs_downsweep_pipe_kernel; rs_downsweep_kernel is the register-prefetch
+//               version kept for unaligned inputs).
 // Per pass HBM traffic: keys read twice, payloads read once, everything written once.
+// radix_sort_segmented sorts every segment of a concatenation independently with the same
+// kernels (tile-sized chunks per segment, segment-major spine).
 #pragma once
 #include <utility>
 #include <vector>

@@ -433,29 +433,14 @@ struct GatherLoader {
 // ---- matrices whose rows all have <= kShortRow entries (stencils, meshes).  One warp owns
 //      32 consecutive NEW rows per step.  Their entries are fetched in concatenated order
 //      (lane s reads the s-th entry of the 32-row batch: consecutive lanes read consecutive
-//      addresses inside a source row), staged in a 2 KB per-warp slice of shared memory,
-//      sorted by the lane that owns the row with a fixed compare-exchange network in
-//      registers, and written back as ONE contiguous, fully coalesced run -- the 32 rows are
-//      adjacent in the output.  No block barriers; three dependent loads per step (row records
-//      -> entries -> renumbered columns). ----
+//      addresses inside a source row), all loads of the batch before the first dependent
+//      col_order gather, staged in a 2 KB per-warp slice of shared memory, ranked inside their
+//      row by enumeration (<= 8 compares) and written straight to their sorted place -- the 32
+//      rows are adjacent in the output, so the warp writes ONE contiguous run.  No block
+//      barriers; three dependent loads per step (row records -> entries -> renumbered
+//      columns). ----
 constexpr int kShortRow = 8;
 constexpr int kSrBlock = 256;
-
-template <typename I, typename V>
-__device__ __forceinline__ void short_cex(I &ka, V &va, I &kb, V &vb) {
-  bool swap = kb < ka;
-  if constexpr (has_val<V>) swap = swap || (kb == ka && vb < va);
-  if (swap) {
-    const I tk = ka;
-    ka = kb;
-    kb = tk;
-    if constexpr (has_val<V>) {
-      const V tv = va;
-      va = vb;
-      vb = tv;
-    }
-  }
-}
 
 template <typename I, typename N, typename V, int MINB>
 __global__ void __launch_bounds__(kSrBlock, MINB)

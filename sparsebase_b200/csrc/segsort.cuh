@@ -10,11 +10,12 @@
 //
 //   segment length <= 32   : rank-by-enumeration, one thread per entry
 //   33 .. kSsLong          : bitonic network run by one warp in shared memory
-//   > kSsLong              : appended to a list; sorted afterwards by the global radix sort
-//                            on the composite key (list rank, index)        (segsort_long)
+//   > kSsLong              : appended to a list; sorted afterwards by a segmented radix sort
+//                            on the index (radix_sort_segmented, see "long segments")
 //
 // Ties (duplicate indices inside a segment) are outside the parity contract; they
-// are ordered deterministically: original order (<=32) or by the value's bit pattern (>32).
+// are ordered deterministically: original order (<=32 and >kSsLong: the sorts are stable) or
+// by the value (33..kSsLong).
 #pragma once
 #include "common.cuh"
 #include "radix_sort.cuh"

@@ -391,8 +391,8 @@ def test_rcm_wide_grids_cluster_regime(sb, orc, shape):
 
 
 def test_permute2d_short_rows_kernel(sb, orc):
-    """Matrices whose longest row has <= 8 entries take the warp-transposed register-sort
-    kernel (reorder.cu permute_short_rows_kernel); empty rows, every type combination."""
+    """Matrices whose longest row has <= 8 entries take the warp-batch kernel
+    (reorder.cu permute_short_rows_kernel); empty rows, every type combination."""
     rng = np.random.default_rng(77)
     n = 50021
     deg = rng.integers(0, 9, size=n)
