@@ -219,14 +219,30 @@ __global__ void __launch_bounds__(kDgBlock)
   const int64_t n = ch.n;
   bin_off[threadIdx.x] = spine[(int64_t)threadIdx.x * ch.nchunks + c];  // kDgBlock == kDgBins
   if (threadIdx.x == 0) high_base = spine[(int64_t)255 * ch.nchunks];
+  // the degrees of the next tile are requested before the current one is ranked
+  // 32-bit degrees when row_ptr is 32-bit: half the registers of the two tiles in flight
+  using DT = typename std::conditional<sizeof(N) == 4, unsigned, unsigned long long>::type;
+  DT nd[kDgIpt];
+  {
+    const int64_t wb = ch.tile_begin(c) * kDgTile + (int64_t)wid * (kDgIpt * 32);
+#pragma unroll
+    for (int r = 0; r < kDgIpt; r++) {
+      const int64_t p = wb + r * 32 + lane;
+      nd[r] = (ch.tile_begin(c) < ch.tile_end(c) && p < n) ? (DT)dg_degree(row_ptr, n, p) : DT(0);
+    }
+  }
   for (int64_t tile = ch.tile_begin(c); tile < ch.tile_end(c); tile++) {
     const int64_t warp_base = tile * kDgTile + (int64_t)wid * (kDgIpt * 32);
     for (int i = threadIdx.x; i < kDgWarps * kDgBins; i += kDgBlock) (&cnt[0][0])[i] = 0;
-    unsigned long long d[kDgIpt];
+    DT d[kDgIpt];
 #pragma unroll
-    for (int r = 0; r < kDgIpt; r++) {
-      const int64_t p = warp_base + r * 32 + lane;
-      d[r] = p < n ? dg_degree(row_ptr, n, p) : 0ull;
+    for (int r = 0; r < kDgIpt; r++) d[r] = nd[r];
+    if (tile + 1 < ch.tile_end(c)) {
+#pragma unroll
+      for (int r = 0; r < kDgIpt; r++) {
+        const int64_t p = warp_base + kDgTile + r * 32 + lane;
+        nd[r] = p < n ? (DT)dg_degree(row_ptr, n, p) : DT(0);
+      }
     }
     __syncthreads();
     // stable rank inside the warp: rounds in order, lanes in order
@@ -234,7 +250,7 @@ __global__ void __launch_bounds__(kDgBlock)
 #pragma unroll
     for (int r = 0; r < kDgIpt; r++) {
       const bool valid = warp_base + r * 32 + lane < n;
-      const unsigned dig = valid ? (d[r] < 255ull ? (unsigned)d[r] : 255u) : 0xffffffffu;
+      const unsigned dig = valid ? (d[r] < DT(255) ? (unsigned)d[r] : 255u) : 0xffffffffu;
       const unsigned peers = __match_any_sync(0xffffffffu, dig);
       const int leader = __ffs(peers) - 1;
       unsigned base = 0;
@@ -262,7 +278,7 @@ __global__ void __launch_bounds__(kDgBlock)
       for (int r = 0; r < kDgIpt; r++) {
         const int64_t p = warp_base + r * 32 + lane;
         if (p < n) {
-          const unsigned dig = d[r] < 255ull ? (unsigned)d[r] : 255u;
+          const unsigned dig = d[r] < DT(255) ? (unsigned)d[r] : 255u;
           const int64_t pos = bin_off[dig] + cnt[wid][dig] + lp[r];
           const int64_t u = n - 1 - p;
           if (dig < 255u) {
