@@ -1,4 +1,4 @@
-"""world_size-2 gloo tests of the multi-GPU host logic (sparsebase_b200/sharded.py) on CPU.
+"""world_size-2 (and 4) gloo tests of the multi-GPU host logic (sparsebase_b200/sharded.py) on CPU.
 
 Each rank runs the sharded operator on its row block with tests/cpu_ops.py standing in for the
 CUDA kernels; rank results are concatenated and compared bit-for-bit with the oracle run on
@@ -92,6 +92,17 @@ def _worker(rank, world, name, initfile, outdir):
 @pytest.mark.parametrize("name", ["poisson", "rmat", "er"])
 def test_sharded_operators_world2_gloo(name):
     world = 2
+    with tempfile.TemporaryDirectory() as d:
+        initfile = os.path.join(d, "init")
+        mp.spawn(_worker, args=(world, name, initfile, d), nprocs=world, join=True)
+        assert all(os.path.exists(os.path.join(d, f"ok{r}")) for r in range(world))
+
+
+@pytest.mark.parametrize("name", ["poisson", "rmat"])
+def test_sharded_operators_world4_gloo(name):
+    """Four ranks: on the banded Poisson matrix distant row blocks exchange nothing (zero-size
+    all_to_all splits); this is the rank count of the driver's scaling runs beyond two."""
+    world = 4
     with tempfile.TemporaryDirectory() as d:
         initfile = os.path.join(d, "init")
         mp.spawn(_worker, args=(world, name, initfile, d), nprocs=world, join=True)
