@@ -334,7 +334,6 @@ def main():
         deg_l = (row_ptr[lo + 1:hi + 1] - row_ptr[lo:hi]).to(torch.int64)
         row_l = torch.repeat_interleave(torch.arange(lo, hi, device=dev, dtype=torch.int32), deg_l)
         col_l, val_l = col[a:b].contiguous(), vals[a:b].contiguous()
-        shard = sharded.coo_to_csr(lib, n, n, bounds, row_l.clone(), col_l.clone(), val_l.clone())
         ops_sharded = {}
 
         def time_sharded(name, fn, reps=3):
@@ -353,7 +352,10 @@ def main():
             ops_sharded[name] = {"ms": ms, "gnnz_per_s": nnz / (ms * 1e-3) / 1e9,
                                  "alg_gb_per_s": gbs, "roofline_frac": gbs / (peak * world)}
 
+        shard = None
         try:  # a failure here must not cost the headline line (the error is reported instead)
+            shard = sharded.coo_to_csr(lib, n, n, bounds, row_l.clone(), col_l.clone(),
+                                       val_l.clone())
             time_sharded("coo_to_csr", lambda: sharded.coo_to_csr(lib, n, n, bounds, row_l, col_l,
                                                                   val_l, copy=False))
             time_sharded("csr_to_csc", lambda: sharded.csr_to_csc(lib, shard))
