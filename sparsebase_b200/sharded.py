@@ -106,6 +106,21 @@ def _exchange_counts(send_counts, device, group=None):
     return [int(x) for x in r.cpu()]
 
 
+_ORDER_CACHE = {}
+
+
+def _interleave_order(world, ncl, dtype, device):
+    """new position c * world + s of segment (source s, column c); a function of the shape only,
+    kept between calls (three elementwise kernels over world * ncl entries otherwise)."""
+    key = (world, ncl, dtype, str(device))
+    if key not in _ORDER_CACHE:
+        if len(_ORDER_CACHE) > 4:
+            _ORDER_CACHE.clear()
+        k = torch.arange(world * ncl, dtype=torch.int64, device=device)
+        _ORDER_CACHE[key] = ((k % ncl) * world + k // ncl).to(dtype)
+    return _ORDER_CACHE[key]
+
+
 def even_bounds(n, world):
     return [n * k // world for k in range(world + 1)]
 
@@ -303,7 +318,9 @@ def csr_to_csc(ops, s: ShardedCSR, group=None):
     tr = _Trace("csr_to_csc")
     cp, rows, vals = ops.csr_to_csc_block(lo, hi - lo, s.m, s.row_ptr, s.col, s.vals)
     tr.mark("local_csc")
-    cnt = (cp[1:] - cp[:-1]).to(torch.int64)
+    # column counts in the pointer type (the global col_ptr has to fit it anyway): for 32-bit
+    # pointers the all_reduce moves half the bytes of an int64 one
+    cnt = cp[1:] - cp[:-1]
     tot = cnt.clone()
     if world > 1:
         dist.all_reduce(tot, group=group)
@@ -318,7 +335,7 @@ def csr_to_csc(ops, s: ShardedCSR, group=None):
     ncl = chi - clo
     recv_cols = [ncl] * world
     recv_nnz = _exchange_counts(send_nnz, dev, group)
-    r_cnt = _all_to_all_var(cnt.to(s.row_ptr.dtype), send_cols, recv_cols, group)
+    r_cnt = _all_to_all_var(cnt, send_cols, recv_cols, group)
     r_row = _all_to_all_var(rows, send_nnz, recv_nnz, group)
     r_val = None if vals is None else _all_to_all_var(vals, send_nnz, recv_nnz, group)
     tr.mark("all_to_all")
@@ -326,8 +343,7 @@ def csr_to_csc(ops, s: ShardedCSR, group=None):
         return ShardedCSC(s.n, s.m, s.nnz, list(cb), cp, rows, vals, 0)
     # segments arrive ordered (source, column); the result needs (column, source)
     seg_ptr = ops.exclusive_scan(r_cnt)
-    k = torch.arange(world * ncl, dtype=s.col.dtype, device=dev)
-    order = ((k % ncl) * world + k // ncl).to(s.col.dtype)           # (s, c) -> c * world + s
+    order = _interleave_order(world, ncl, s.col.dtype, dev)          # (s, c) -> c * world + s
     tr.mark("order")
     o_ptr, o_row, o_val = ops.permute2d(world * ncl, s.n, seg_ptr, r_row, r_val, order, None)
     tr.mark("interleave")
