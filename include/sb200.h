@@ -41,8 +41,9 @@
  *    bit-exactly and never interpreted (except as a tie-break key, see sb200_compressed_sort).
  *    Index values must be non-negative and below 2^31 (4-byte) / 2^62 (8-byte).
  *  - `stream` is a cudaStream_t (NULL = the legacy default stream).  Calls are asynchronous
- *    with respect to the host unless stated otherwise; scratch memory comes from the
- *    stream-ordered CUDA memory pool of `device`.
+ *    with respect to the host unless stated otherwise; scratch memory comes from a private
+ *    stream-ordered memory pool of `device` (see sb200_trim).  A call never changes the
+ *    calling thread's current device.
  *  - There is NO CPU fallback anywhere in this library: without a CUDA device every compute
  *    entry point fails with SB200_ERR_CUDA.
  */
@@ -94,6 +95,11 @@ int sb200_memcpy_d2h(int device, void *h_dst, const void *src, size_t bytes, voi
 int sb200_memcpy_d2d(int dst_device, void *dst, int src_device, const void *src, size_t bytes,
                      void *stream);
 int sb200_stream_synchronize(int device, void *stream);
+/* Scratch memory comes from a private stream-ordered pool per device that keeps freed blocks
+ * for the next call.  sb200_trim synchronises the device and returns those blocks to the
+ * driver (call it before another allocator needs the memory, e.g. after a one-off large
+ * conversion).  The device's default memory pool is never touched by this library. */
+int sb200_trim(int device);
 
 /* ---- format constructors ---- */
 
@@ -144,17 +150,19 @@ int sb200_rcm_reorder(int device, int64_t n, int64_t nnz, const void *row_ptr, c
                       void *out_inv, int id_type, int nnz_type, void *stream);
 
 /* Diagnostics of the last sb200_rcm_reorder call made by the calling thread:
- * h_out4 = {levels walked by the persistent single-CTA kernel, levels done with grid-wide
+ * h_out4 = {levels walked by the persistent cluster kernel, levels done with grid-wide
  * kernels, number of BFS traversals, number of non-trivial connected components}. */
 int sb200_rcm_last_stats(int64_t *h_out4);
+/* h_out2 = {times the cluster re-split the frontier evenly over its CTAs, times the kernel was
+ * relaunched with another cluster size}. */
+int sb200_rcm_last_resplits(int64_t *h_out2);
 /* The BFS traversals of peripheral() after the first are run as the Cuthill-McKee traversal
  * itself (same level sets).  h_out3 = {confirmed: eccentricity did not grow, one BFS saved;
  * continued: it grew and the new root was unique by degree, no replay needed; replayed: it grew
  * and the new root depended on the FIFO order, the BFS was repeated literally}. */
 int sb200_rcm_last_speculation(int64_t *h_out3);
-/* SM-cycle counters of the narrow regime's per-level phases {seek, claim, barrier 1, recheck,
- * compaction, count exchange (barrier 2), sibling sort + queue write, degree rescan}
- * accumulated by CTA 0 (profiling aid). */
+/* SM-cycle counters of the narrow regime's per-level phases {claims, cluster barrier, recheck,
+ * compaction, sibling sort + state update, 0, 0, 0} accumulated by CTA 0 (profiling aid). */
 int sb200_rcm_last_cycles(int64_t *h_out8);
 
 /* ---- applying a permutation ---- */

@@ -51,7 +51,35 @@ struct Error {
     SB_CUDA(cudaGetLastError());                                               \
   } while (0)
 
-// Wraps the body of an extern "C" entry point: selects the device, converts exceptions to codes.
+// Selects `device` for the lifetime of the object and puts the caller's current device back
+// afterwards (also when the body throws): an entry point never changes the calling thread's
+// device, so a call on cuda:1 made while cuda:0 is current leaves cuda:0 current.
+class DeviceScope {
+ public:
+  explicit DeviceScope(int device) {
+    if (cudaGetDevice(&prev_) != cudaSuccess) prev_ = -1;
+    if (prev_ != device) {
+      cudaError_t e = cudaSetDevice(device);
+      if (e != cudaSuccess) {
+        set_error("cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(e));
+        throw Error{SB200_ERR_CUDA};
+      }
+      switched_ = true;
+    }
+  }
+  ~DeviceScope() {
+    if (switched_ && prev_ >= 0) cudaSetDevice(prev_);
+  }
+  DeviceScope(const DeviceScope &) = delete;
+  DeviceScope &operator=(const DeviceScope &) = delete;
+
+ private:
+  int prev_ = -1;
+  bool switched_ = false;
+};
+
+// Wraps the body of an extern "C" entry point: selects the device (restoring the caller's on
+// the way out), converts exceptions to codes.
 template <typename Fn>
 int guarded(int device, Fn &&fn) {
   try {
@@ -66,7 +94,7 @@ int guarded(int device, Fn &&fn) {
       set_error("device %d out of range (device count %d)", device, cnt);
       return SB200_ERR_BAD_DEVICE;
     }
-    SB_CUDA(cudaSetDevice(device));
+    DeviceScope scope(device);
     fn();
     return SB200_OK;
   } catch (const Error &err) {
@@ -89,8 +117,11 @@ struct DeviceInfo {
 const DeviceInfo &device_info(int device);
 
 // ---------------------------------------------------------------- scratch memory
-// Stream-ordered scratch (cudaMallocAsync on the device's default pool, release threshold
-// raised so that repeated calls re-use the same blocks without touching the driver).
+// Stream-ordered scratch from a PRIVATE memory pool per device (cudaMallocFromPoolAsync; the
+// release threshold of that pool is raised so that repeated calls re-use the same blocks
+// without touching the driver).  The device's default pool -- shared with every other library
+// in the process -- is left alone; sb200_trim(device) hands the cached blocks back.
+cudaMemPool_t scratch_pool(int device);
 class Workspace {
  public:
   Workspace(int device, cudaStream_t stream);
@@ -106,6 +137,7 @@ class Workspace {
  private:
   int device_;
   cudaStream_t stream_;
+  cudaMemPool_t pool_;
   std::vector<void *> ptrs_;
 };
 
@@ -236,6 +268,43 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T *warp_sums, T *total = 
   if (total) *total = warp_sums[32];
   return warp_sums[wid] + inc - v;
 }
+
+// Values travel through the kernels as bit patterns (uint32_t / uint64_t).  Where the reference
+// COMPARES values -- std::less<std::pair<IDType, ValueType>> on duplicate ids, csr.cc:147 -- the
+// pattern is mapped to an unsigned key that orders like the real type `vkind` (an SB200_* code):
+// floats: negative values reversed below the positive ones; signed integers: sign bit flipped.
+template <typename V>
+__device__ __forceinline__ V val_order_key(V bits, int vkind) {
+  constexpr V sign = V(1) << (sizeof(V) * 8 - 1);
+  if (vkind == SB200_F32 || vkind == SB200_F64) return (bits & sign) ? V(~bits) : V(bits | sign);
+  if (vkind == SB200_I32 || vkind == SB200_I64) return V(bits ^ sign);
+  return bits;
+}
+
+// Duplicate ids inside a segment (outside the reference's own input contract, but its result is
+// still defined): the reference sorts EVERY segment by (id, value) as soon as ANY segment is
+// unsorted, and otherwise leaves all of them untouched (csr.cc:99-157).  The fast kernels order
+// ties arbitrarily, flag the segments that hold duplicates and report whether any segment was
+// unsorted in source order; dup_fix_kernel (segsort.cuh) then puts the flagged segments right.
+struct DupCtx {
+  unsigned char *seg_flag;  // [n_seg], zeroed: 1 = the segment holds duplicate ids
+  unsigned *any_dup;        // zeroed: some segment is flagged
+  unsigned *unsorted;       // zeroed: some segment had an inversion in source order
+                            // (null: the caller knows the sort happens)
+  __device__ __forceinline__ void flag(int64_t seg) const {
+    if (seg_flag) {
+      seg_flag[seg] = 1;
+      *reinterpret_cast<volatile unsigned *>(any_dup) = 1u;
+    }
+  }
+  // call with a block-uniform predicate per thread; contains __syncthreads_or
+  __device__ __forceinline__ void report_unsorted(bool mine) const {
+    const int any = __syncthreads_or(mine ? 1 : 0);
+    if (unsorted && any && threadIdx.x == 0 &&
+        *reinterpret_cast<volatile unsigned *>(unsorted) == 0u)
+      *reinterpret_cast<volatile unsigned *>(unsorted) = 1u;
+  }
+};
 
 // streaming (read-once / write-once) accesses: keep them out of L1
 template <typename T>

@@ -349,9 +349,11 @@ bool compressed_check(Workspace &ws, const N *ptr, const I *idx, int64_t n_seg) 
 
 template <typename I, typename N, typename V>
 void compressed_sort_inplace(Workspace &ws, const N *ptr, I *idx, V *vals, int64_t n_seg,
-                             int64_t n_idx, int64_t nnz) {
+                             int64_t n_idx, int64_t nnz, int vkind) {
+  // the caller ran the constructor's check: some segment is unsorted, so EVERY segment is
+  // sorted by (index, value) -- values compared in their real type `vkind`
   InPlaceLoader<I, N, V> ld{ptr, idx, vals};
-  segmented_sort<I, N, V>(ws, ld, ptr, n_seg, n_idx, nnz, idx, vals);
+  segmented_sort<I, N, V>(ws, ld, ptr, n_seg, n_idx, nnz, idx, vals, vkind, true);
 }
 
 // =====================================================================================
@@ -570,7 +572,7 @@ void expand_ptr(Workspace &ws, const N *ptr, int64_t n_seg, int64_t nnz, const I
 // =====================================================================================
 template <typename I, typename N, typename V>
 void to_csc_core(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const I *row, const I *col,
-                 const V *vals, N *out_col_ptr, I *out_row, V *out_vals,
+                 const V *vals, N *out_col_ptr, I *out_row, V *out_vals, int vkind,
                  bool rows_ascending = false) {
   // n = number of col_ptr segments: dims[0] for the reference layout (square assumption),
   // m for the row-block variant used by the multi-GPU path
@@ -609,9 +611,9 @@ void to_csc_core(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const I *row,
                                   nullptr, nnz, n, out_col_ptr, nullptr, nullptr, h_flags);
   if (h_flags[1]) {  // csc.cc:99-157: some column has unsorted rows -> sort every column
     if constexpr (has_val<V>)
-      compressed_sort_inplace<I, N, V>(ws, out_col_ptr, out_row, out_vals, n, n, nnz);
+      compressed_sort_inplace<I, N, V>(ws, out_col_ptr, out_row, out_vals, n, n, nnz, vkind);
     else
-      compressed_sort_inplace<I, N, NoVal>(ws, out_col_ptr, out_row, nullptr, n, n, nnz);
+      compressed_sort_inplace<I, N, NoVal>(ws, out_col_ptr, out_row, nullptr, n, n, nnz, vkind);
   }
 }
 
@@ -652,7 +654,7 @@ int sb200_compressed_sort(int device, int64_t n_seg, int64_t n_idx, int64_t nnz,
       if (h_was_sorted) *h_was_sorted = sorted ? 1 : 0;
       if (!sorted)
         compressed_sort_inplace<I, N, V>(ws, (const N *)ptr, (I *)idx, (V *)vals, n_seg, n_idx,
-                                         nnz);
+                                         nnz, val_type);
     });
   });
 }
@@ -679,7 +681,7 @@ int sb200_coo_to_csr(int device, int64_t n, int64_t m, int64_t nnz, const void *
         need_sort = !compressed_check<I, N, V>(ws, (const N *)out_row_ptr, (const I *)out_col, n);
       if (need_sort)
         compressed_sort_inplace<I, N, V>(ws, (const N *)out_row_ptr, (I *)out_col,
-                                         (V *)out_vals, n, m, nnz);
+                                         (V *)out_vals, n, m, nnz, val_type);
     });
   });
 }
@@ -717,7 +719,7 @@ int sb200_coo_to_csc(int device, int64_t n, int64_t m, int64_t nnz, const void *
       using N = decltype(N_);
       using V = decltype(V_);
       to_csc_core<I, N, V>(ws, n, m, nnz, (const I *)row, (const I *)col, (const V *)vals,
-                           (N *)out_col_ptr, (I *)out_row, (V *)out_vals);
+                           (N *)out_col_ptr, (I *)out_row, (V *)out_vals, val_type);
     });
   });
 }
@@ -742,7 +744,7 @@ int sb200_csr_to_csc(int device, int64_t n, int64_t m, int64_t nnz, const void *
       expand_ptr<I, N, NoVal>(ws, (const N *)row_ptr, n, nnz, (const I *)nullptr,
                               (const NoVal *)nullptr, rows, (I *)nullptr, (NoVal *)nullptr);
       to_csc_core<I, N, V>(ws, n, m, nnz, rows, (const I *)col, (const V *)vals,
-                           (N *)out_col_ptr, (I *)out_row, (V *)out_vals, true);
+                           (N *)out_col_ptr, (I *)out_row, (V *)out_vals, val_type, true);
     });
   });
 }
@@ -773,7 +775,7 @@ int sb200_coo_to_csr_block(int device, int64_t row_lo, int64_t n_local, int64_t 
             !compressed_check<I, N, V>(ws, (const N *)out_row_ptr, (const I *)out_col, n_local);
       if (need_sort)
         compressed_sort_inplace<I, N, V>(ws, (const N *)out_row_ptr, (I *)out_col,
-                                         (V *)out_vals, n_local, m, nnz);
+                                         (V *)out_vals, n_local, m, nnz, val_type);
     });
   });
 }
@@ -798,7 +800,7 @@ int sb200_csr_to_csc_block(int device, int64_t row_lo, int64_t n_local, int64_t 
                               (I)row_lo);
       // col_ptr gets m+1 entries here (one per global column)
       to_csc_core<I, N, V>(ws, m, m, nnz, rows, (const I *)col, (const V *)vals,
-                           (N *)out_col_ptr, (I *)out_row, (V *)out_vals, true);
+                           (N *)out_col_ptr, (I *)out_row, (V *)out_vals, val_type, true);
     });
   });
 }

@@ -9,28 +9,36 @@
 //     (degree, id) -> next level == newly reached vertices sorted by (queue position of the
 //     first parent, degree, id) -> atomicMin of the parent position, then a per-parent sort.
 //
+// mark[v] (64 bits) is the claim key of v's first discoverer: (level << 32) | position.  Keys
+// grow from level to level, so a vertex reached earlier always holds a SMALLER mark than any
+// later claim: no separate "visited" store exists, and both regimes share the array.
+//
 // Two execution regimes share all global state (mark[], the queues, RcmState):
-//   NARROW  one persistent 1024-thread CTA walks levels without returning to the host while
-//           the frontier fits shared memory (high-diameter graphs: grids, bands -- thousands
-//           to millions of levels); warp-cooperative neighbour expansion, claims by atomicMin
-//           in L2, ordered compaction by warp prefix sums, sibling sort by enumeration.
+//   NARROW  one persistent thread-block cluster (1, 2, 4, 8 or 16 CTAs, chosen from the frontier
+//           width) walks levels without returning to the host while the frontier fits shared
+//           memory (high-diameter graphs: grids, bands -- thousands to millions of levels).
 //   WIDE    one level at a time driven by the host with grid-wide kernels (power-law / random
 //           graphs: a handful of levels, millions of vertices): exclusive scan of frontier
-//           degrees, claim sweep, collect sweep, radix sort on the level's order key, commit.
+//           degrees, claim sweep, collect sweep, radix sort on the level's order key.
 // The persistent kernel is a resumable state machine: when a level does not fit it stores its
-// state and returns NEED_WIDE (or NEED_RESET / NEED_INVERT for bulk array work); the host runs
-// that step with all SMs and relaunches it.
+// state and returns NEED_WIDE (or NEED_RESET / NEED_INVERT for bulk array work, NEED_RESIZE to be
+// relaunched with another cluster size); the host runs that step and relaunches it.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
 
 namespace sb200 {
+namespace cg = cooperative_groups;
 
-constexpr unsigned kUnvisited = 0xffffffffu;
+constexpr unsigned long long kUnvisited = ~0ull;
 constexpr int kNwBlock = 512;
 constexpr int kNwWarps = kNwBlock / 32;
-constexpr int kNwGroupCap = 96;     // max degree in a CM frontier (bounds sibling groups)
-constexpr int64_t kBulkThreshold = 1 << 15;  // resets / inversions larger than this go wide
+constexpr int kRounds = 4;                      // 32-slot rounds per warp and level, at most
+constexpr int kPadCap = kNwBlock * kRounds;     // padded expansion slots per CTA and level
+constexpr int64_t kBulkThreshold = 1 << 15;     // resets / inversions larger than this go wide
+constexpr int kClMax = 16;
 
 enum RcmPhase {
   PH_FIND = 0,
@@ -44,7 +52,14 @@ enum RcmPhase {
   PH_CM_AFTER_INVERT,
   PH_DONE
 };
-enum RcmStatus { ST_RUNNING = 0, ST_DONE, ST_NEED_WIDE, ST_NEED_RESET, ST_NEED_INVERT };
+enum RcmStatus {
+  ST_RUNNING = 0,
+  ST_DONE,
+  ST_NEED_WIDE,
+  ST_NEED_RESET,
+  ST_NEED_INVERT,
+  ST_NEED_RESIZE
+};
 
 struct RcmState {
   int64_t next_i;      // component scan position (rcm_reorder.cc:104)
@@ -59,38 +74,41 @@ struct RcmState {
   int32_t status;
   int32_t next_phase_after_reset;
   int32_t spec;  // 1: the running CM BFS stands in for a BFS of peripheral() (PH_PBFS_END)
-  int64_t frontier_maxdeg;  // max degree over the current frontier (for the narrow caps)
-  int64_t key_base;    // peripheral BFS: expansion slots of all earlier levels (monotone claim keys)
+  int64_t frontier_maxdeg;  // max degree over the current frontier (sizes the narrow regime)
+  int64_t resize_to;   // ST_NEED_RESIZE: cluster size the kernel asks for
   int64_t inv_qst, inv_end;  // pending bulk inversion
   int64_t reset_cm;    // pending bulk reset walks Q[qst, lvl_end) instead of Qp[0, lvl_end)
   int64_t stat_spec_ok, stat_spec_fail, stat_spec_chain;
   int64_t stat_levels_narrow, stat_levels_wide, stat_bfs, stat_components;
-  int64_t cyc[8];  // narrow-level phase cycle counters (CTA 0): load, claim, check, finalize, write
+  int64_t stat_reloads, stat_resizes;
+  int64_t cyc[8];  // narrow-level phase cycle counters (CTA 0): claim, barrier, recheck,
+                   // compaction, sibling sort + state
 };
-
-__device__ __forceinline__ int bits_for_dev(unsigned long long v) {
-  return v ? 64 - __clzll((long long)v) : 0;
-}
 
 template <typename I, typename N>
 struct RcmArgs {
   int64_t n;
   const N *xadj;
   const I *adj;
-  unsigned *mark;
+  unsigned long long *mark;
   I *Q;    // CM order (reference: Q), concatenated components, not yet reversed
   I *Qp;   // peripheral BFS queue (reference: Qp)
   I *inv;  // result: inv[Qp2[i]] = i
   RcmState *state;
   int force_wide;  // testing: never take the narrow path
   int no_spec;     // testing: never run a peripheral BFS speculatively as the CM BFS
+  // cluster sizing (0 = fixed size): grow / shrink when the running mean of the padded
+  // expansion slots per CTA and level leaves [shrink_below, grow_above]; aim at `target`
+  int max_cluster;
+  int grow_above, shrink_below, target;
+  int profile;  // accumulate the per-phase cycle counters (SB200_RCM_PROFILE=1)
 };
 
 // ------------------------------------------------------------------------------------
-// Warp-cooperative expansion of a group of (up to) 32 frontier vertices.  Lane l holds the
-// adjacency start xs and degree d of vertex g+l; the warp walks the concatenated adjacency
-// lists 32 slots at a time.  f(slot_in_group, owner_lane, adjacency_position, valid) is called
-// once per round by every lane (valid == false for the padding of the last round).
+// Warp-cooperative expansion of a group of (up to) 32 frontier vertices (WIDE regime).  Lane l
+// holds the adjacency start xs and degree d of vertex g+l; the warp walks the concatenated
+// adjacency lists 32 slots at a time.  f(slot_in_group, owner_lane, adjacency_position, valid)
+// is called once per round by every lane (valid == false for the padding of the last round).
 // ------------------------------------------------------------------------------------
 template <typename Fn>
 __device__ __forceinline__ void warp_expand(int64_t xs, unsigned d, Fn &&f) {
@@ -114,76 +132,75 @@ __device__ __forceinline__ void warp_expand(int64_t xs, unsigned d, Fn &&f) {
 }
 
 // ------------------------------------------------------------------------------------
-// NARROW regime: one thread-block CLUSTER walks the levels.
+// NARROW regime: one thread-block CLUSTER walks the levels, ONE cluster barrier per level.
 //
-// A single SM cannot issue the ~3 scattered L2 accesses per edge of a 4096-wide level fast
-// enough (measured: 36 us per level, LSU-bound), so the level is split over the CTAs of one
-// cluster (16 where the device allows it, else 8).  Every CTA keeps ITS share of the frontier
-// in shared memory from one level to the next: the vertices it discovers (already sorted,
-// with their adjacency extents) are its share of the next level, so a level needs no global
-// re-read and only two cluster barriers:
-//     claims (atomicMin in L2)            -> barrier 1 ->
-//     recheck, compaction, sibling sort   -> exchange of the per-CTA counts (barrier 2)
-// The global queue is still written every level (it is the result), but nobody waits for it.
-// Shares drift apart over time (a BFS starts with everything in CTA 0); when the largest
-// share exceeds twice the even share, or shared memory, the CTAs re-split the frontier evenly
-// from the global queue (cl_reload, one more barrier).
+// Every CTA keeps ITS share of the frontier in shared memory from one level to the next: the
+// vertices it discovers (already ordered, with their adjacency extents) are its share of the
+// next level, and the shares of the CTAs, taken in rank order, are the frontier in queue order.
+// A level is
+//     claims     every thread owns up to kRounds expansion slots of the share (slot = vertex i
+//                of the share x adjacency index j, padded to the share's largest degree D so
+//                that i = slot / D needs no search), loads the neighbour and claims it with
+//                atomicMin(mark, key).  key = (level << 32) | (CTA rank << 16) | position is
+//                order-isomorphic to the reference's queue position and needs nothing from the
+//                other CTAs.  A thread REMEMBERS its claims in registers.
+//     barrier    all claims of the level have landed.  The same barrier carries the exchange of
+//                the share sizes (one remote shared-memory store per CTA pair before it).
+//     recheck    a claim survived iff the mark still equals its key; the same round trip fetches
+//                the winner's adjacency extent.  Winners are compacted in slot order (ballots +
+//                one cross-warp prefix) and, for Cuthill-McKee, ranked inside their sibling
+//                group by (degree, id): that IS the CTA's share of the next level.
+// The share is written to the global queue (the result) one level late, when the share sizes of
+// the lower-ranked CTAs are known; nobody waits for it.
+// Shares drift apart over time (a BFS starts with everything in CTA 0); when the largest share
+// exceeds twice the even share, or a share no longer fits kPadCap slots, the CTAs re-split the
+// frontier evenly from the global queue (cl_reload).  A share that does not fit announces it in
+// the exchange and makes no claims; the other CTAs take their claims of that level back
+// (cl_level abort path), so the level can be repeated after the re-split or by the WIDE regime.
 // All CTAs run the same state machine on replicated state, so control flow is uniform.
 // ------------------------------------------------------------------------------------
-constexpr int kClMax = 16;
-// expansion slots (and provisional / final winners) per CTA and level; 8-byte ids get fewer so
-// that the staging arrays stay inside the 227 KB of shared memory
-constexpr int kEl = 4096;
-constexpr int kEl64 = 3072;
-template <typename I>
-constexpr int cl_el() {
-  return sizeof(I) == 4 ? kEl : kEl64;
-}
-constexpr int kFl = 1024;  // frontier vertices per CTA and level
-constexpr int kClBatch = 4;  // 32-slot rounds whose loads are in flight together
-
 template <typename I>
 struct ClSmem {
   // this CTA's share of the current frontier: vertex, adjacency start, degree
-  I F[kFl];
-  int64_t Fx[kFl];
-  unsigned Fd[kFl];
-  // provisional winners of sweep 1, one region per warp (region base = prefix of wslot[])
-  I pv[cl_el<I>()];
-  unsigned pkey[cl_el<I>()];  // claim key; 0 after sweep 2 when the claim lost
-  unsigned pi[cl_el<I>()];    // local index of the parent in F
-  int64_t px[cl_el<I>()];     // adjacency start / degree of the claimed vertex (filled by sweep 2)
-  unsigned pd[cl_el<I>()];
-  // final winners in slot order
-  I cv[cl_el<I>()];
-  unsigned ci[cl_el<I>()];
-  unsigned cd[cl_el<I>()];
-  int64_t cx[cl_el<I>()];
-  unsigned long long xch[2][kClMax][4];
+  I Fv[kPadCap];
+  int64_t Fx[kPadCap];
+  unsigned Fd[kPadCap];
+  // Cuthill-McKee: the winners in slot order, before the sibling sort (+ parent's share index)
+  I Sv[kPadCap];
+  int64_t Sx[kPadCap];
+  unsigned Sd[kPadCap];
+  unsigned Sp[kPadCap];
+  unsigned long long lx[2][kClMax];      // per-level exchange: share size | D << 16 | flags
+  __align__(8) unsigned long long lxbar[2];  // mbarriers: all records of a level have arrived
+  unsigned long long xch[2][kClMax][4];  // generic exchange (component search)
   unsigned long long mine[4];
-  unsigned wtot[kNwWarps + 2];
-  unsigned wslot[kNwWarps];  // expansion slots of each warp's part of the share
-  unsigned wprov[kNwWarps];
   unsigned wwin[kNwWarps];
   unsigned wmax[kNwWarps];
-  unsigned wsum[kNwWarps];
+  unsigned wtot[kNwWarps + 2];
   unsigned scratch[34];
   unsigned long long red[kNwWarps];
-  int fl;        // share size
-  long long fb;  // global frontier position of F[0]
-  unsigned sbase;  // expansion slots of the shares of the lower-ranked CTAs (this level)
-  // replicated: largest number of expansion slots of any share, slots of the whole level;
-  // need_reload = 1: the shares must be re-split from the global queue
-  unsigned long long max_slots;
-  unsigned long long level_slots;
-  int need_reload;
+  int fl;           // share size
+  unsigned D;       // largest degree in the share (>= 1): padded slots per vertex
+  unsigned invD;    // ceil(2^32 / D), for slot / D (unused when D == 1)
+  unsigned rounds;  // 32-slot rounds per warp this level; > kRounds: the share does not fit
+  // replicated (identical in every CTA):
+  int need_reload;    // re-split the frontier from the global queue before the next level
+  int share_written;  // the current frontier is in the global queue and S.lvl_end is known
+  int just_reloaded;  // the shares are an even split: if they still do not fit, go wide
+  int want_resize;    // ask the host for this cluster size before the next level
+  int since_resize;
+  unsigned long long work_acc;  // 16 x running mean of the padded slots per level
   RcmState S;
 };
 
-}  // namespace sb200
-#include <cooperative_groups.h>
-namespace sb200 {
-namespace cg = cooperative_groups;
+constexpr unsigned long long kLxNoFit = 1ull << 48;
+
+__device__ __forceinline__ void cl_sync(cg::cluster_group &cluster, unsigned C) {
+  if (C == 1)
+    __syncthreads();
+  else
+    cluster.sync();
+}
 
 // Every CTA contributes s.mine[0..3]; afterwards s.xch[par][k][*] holds CTA k's values in every
 // CTA.  Contains a cluster barrier.  `par` alternates so that a fast CTA never overwrites
@@ -199,334 +216,419 @@ __device__ __forceinline__ void cl_exchange(cg::cluster_group &cluster, ClSmem<I
     dst[2] = s.mine[2];
     dst[3] = s.mine[3];
   }
-  cluster.sync();
+  cl_sync(cluster, C);
   par ^= 1;
 }
 
-// Warp w expands the share's vertices [fl*w/W, fl*(w+1)/W).
-__device__ __forceinline__ int cl_part_begin(int fl, unsigned w) {
-  return (int)(((long long)fl * w) / kNwWarps);
-}
-
-// Per-warp expansion-slot totals of the share F[0..fl) -> s.wslot[]; returns the CTA total.
-// Contains __syncthreads().
+// thread 0: the share now has fl vertices of degree <= dmax
 template <typename I>
-__device__ __forceinline__ unsigned cl_count_slots(ClSmem<I> &s, int fl) {
-  const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
-  unsigned sum = 0;
-  for (int i = cl_part_begin(fl, wid) + (int)lane; i < cl_part_begin(fl, wid + 1); i += 32)
-    sum += s.Fd[i];
-  sum = warp_reduce_sum(sum);
-  if (lane == 0) s.wslot[wid] = sum;
-  __syncthreads();
-  unsigned total = 0;
-#pragma unroll
-  for (int w = 0; w < kNwWarps; w++) total += s.wslot[w];
-  return total;
+__device__ __forceinline__ void cl_set_shape(ClSmem<I> &s, int fl, unsigned dmax) {
+  const unsigned D = dmax > 0u ? dmax : 1u;
+  s.fl = fl;
+  s.D = D;
+  s.invD = D > 1u ? 0xffffffffu / D + 1u : 0u;
+  const unsigned long long total = (unsigned long long)fl * D;
+  s.rounds = total > (unsigned long long)kPadCap ? (unsigned)kRounds + 1u
+                                                 : (unsigned)((total + kNwBlock - 1) / kNwBlock);
 }
 
-// Re-split the frontier queue[lvl_begin, lvl_end) evenly over the CTAs (also the way a BFS
-// starts and the way the kernel resumes after a host-driven step).  Contains cluster barriers.
+struct LxSum {
+  unsigned cbase, ctotal, cmax, dmax;
+  bool nofit;
+};
+
+__device__ __forceinline__ unsigned cl_smem_u32(const void *p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+
+// Per-level exchange AND synchronisation of the cluster in one step.  Every CTA sends its record
+// (share size | D << 16 | no-fit flag) into slot [rank] of every CTA's lx[par] with st.async,
+// which completes bytes on the RECEIVER's mbarrier; a CTA passes when the records of all C CTAs
+// have landed in its own shared memory.  A CTA sends after its claims of the level have been
+// performed (their results are consumed before the block barrier below), so passing also means
+// "all claims of the level have landed" -- without the GPU-scope fence and L1 invalidation that
+// barrier.cluster costs (MEMBAR.ALL.GPU + CCTL.IVALL, 1600 cycles per level measured).
+// lxstate: bit 0 = buffer / barrier to use, bits 1-2 = phase parity of the two barriers.
+template <typename I, typename Between>
+__device__ __forceinline__ LxSum cl_lx_exchange(ClSmem<I> &s, unsigned C, unsigned rank,
+                                                bool fits, unsigned &lxstate, Between &&between) {
+  const unsigned d = s.D > 0xffffffu ? 0xffffffu : s.D;
+  // (share sizes never exceed kPadCap < 2^16)
+  const unsigned long long rec = (unsigned long long)(unsigned)s.fl |
+                                 ((unsigned long long)d << 16) | (fits ? 0ull : kLxNoFit);
+  LxSum r = {0u, 0u, 0u, 0u, false};
+  if (C == 1u) {  // nobody to talk to
+    const unsigned fl = (unsigned)s.fl;
+    __syncthreads();
+    between();
+    r.ctotal = r.cmax = fl;
+    r.dmax = fl > 0u ? d : 0u;
+    r.nofit = !fits;
+    return r;
+  }
+  const unsigned par = lxstate & 1u;
+  __syncthreads();  // every warp's claims are done
+  if (threadIdx.x < C) {
+    unsigned raddr, rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                 : "=r"(raddr)
+                 : "r"(cl_smem_u32(&s.lx[par][rank])), "r"(threadIdx.x));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                 : "=r"(rbar)
+                 : "r"(cl_smem_u32(&s.lxbar[par])), "r"(threadIdx.x));
+    asm volatile(
+        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr),
+        "l"(rec), "r"(rbar)
+        : "memory");
+  } else if (threadIdx.x == 32) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                     cl_smem_u32(&s.lxbar[par])),
+                 "r"(C * 8u)
+                 : "memory");
+  }
+  {
+    const unsigned phase = (lxstate >> (1u + par)) & 1u;
+    unsigned ok;
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(cl_smem_u32(&s.lxbar[par])), "r"(phase)
+          : "memory");
+    } while (!ok);
+  }
+  lxstate ^= 1u | (2u << par);
+  between();
+  // lane k holds CTA k's record
+  const unsigned lane = lane_id();
+  unsigned cnt = 0, dd = 0, nf = 0;
+  if (lane < C) {
+    const unsigned long long x = s.lx[par][lane];
+    cnt = (unsigned)(x & 0xffffull);
+    dd = cnt > 0u ? (unsigned)((x >> 16) & 0xffffffffull) : 0u;
+    nf = (x & kLxNoFit) != 0ull ? 1u : 0u;
+  }
+  r.cbase = __reduce_add_sync(0xffffffffu, lane < rank ? cnt : 0u);
+  r.ctotal = __reduce_add_sync(0xffffffffu, cnt);
+  r.cmax = __reduce_max_sync(0xffffffffu, cnt);
+  r.dmax = __reduce_max_sync(0xffffffffu, dd);
+  r.nofit = __any_sync(0xffffffffu, nf != 0u);
+  return r;
+}
+
+// The shares hold a frontier that is not in the global queue yet: exchange the sizes, write it.
+// Contains a cluster barrier; the queue writes are visible to the other CTAs after the next one.
+template <typename I>
+__device__ void cl_flush_share(cg::cluster_group &cluster, ClSmem<I> &s, I *queue,
+                               unsigned &lxstate) {
+  const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
+  const LxSum x = cl_lx_exchange(s, C, rank, true, lxstate, [] {});
+  for (int k = threadIdx.x; k < s.fl; k += kNwBlock) queue[s.S.lvl_begin + x.cbase + k] = s.Fv[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s.S.lvl_end = s.S.lvl_begin + x.ctotal;
+    s.S.frontier_maxdeg = x.dmax;
+    s.share_written = 1;
+  }
+  __syncthreads();
+}
+
+// Re-split the frontier queue[lvl_begin, lvl_end) evenly over the CTAs (also the way the kernel
+// resumes after a host-driven step).  Contains cluster barriers.
 template <typename I, typename N>
 __device__ void cl_reload(cg::cluster_group &cluster, const RcmArgs<I, N> &a, ClSmem<I> &s,
-                          const I *queue, int &par) {
+                          I *queue, unsigned &lxstate) {
   const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
-  cluster.sync();  // every CTA's queue writes of the previous level are visible
+  const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
+  if (!s.share_written) cl_flush_share(cluster, s, queue, lxstate);
+  cl_sync(cluster, C);  // every CTA's queue writes are visible
   const int64_t f = s.S.lvl_end - s.S.lvl_begin;
-  const int64_t max_share = (f + C - 1) / C;
-  int fl = 0;
-  long long fb = 0;
-  unsigned total = 0;
-  if (max_share <= kFl) {
-    fb = f * rank / C;
-    fl = (int)(f * (rank + 1) / C - fb);
-    for (int i = threadIdx.x; i < fl; i += kNwBlock) {
+  const int64_t fb = f * rank / C;
+  int64_t fl = f * (rank + 1) / C - fb;
+  unsigned dmax = 0;
+  if (fl > kPadCap) {
+    fl = 0;
+    dmax = 0xffffffffu;  // does not fit whatever the degrees are
+  } else {
+    for (int i = threadIdx.x; i < (int)fl; i += kNwBlock) {
       const I v = __ldcg(queue + s.S.lvl_begin + fb + i);
       const int64_t xs = (int64_t)a.xadj[v];
-      s.F[i] = v;
+      const unsigned d = (unsigned)((int64_t)a.xadj[v + 1] - xs);
+      s.Fv[i] = v;
       s.Fx[i] = xs;
-      s.Fd[i] = (unsigned)((int64_t)a.xadj[v + 1] - xs);
+      s.Fd[i] = d;
+      dmax = d > dmax ? d : dmax;
     }
-    __syncthreads();
-    total = cl_count_slots(s, fl);
   }
+  dmax = __reduce_max_sync(0xffffffffu, dmax);
+  if (lane == 0) s.wmax[wid] = dmax;
+  __syncthreads();
   if (threadIdx.x == 0) {
-    s.fl = fl;
-    s.fb = fb;
-    s.mine[0] = max_share <= kFl ? total : (unsigned long long)cl_el<I>() + 1;  // too wide: go wide
-    s.mine[1] = s.mine[2] = s.mine[3] = 0;
-  }
-  cl_exchange(cluster, s, par);
-  unsigned long long mx = 0, sum = 0, below = 0;
-  for (unsigned k = 0; k < C; k++) {
-    const unsigned long long tk = s.xch[par ^ 1][k][0];
-    mx = tk > mx ? tk : mx;
-    sum += tk;
-    below += k < rank ? tk : 0ull;
-  }
-  if (threadIdx.x == 0) {
-    s.max_slots = mx;
-    s.level_slots = sum;
-    s.sbase = (unsigned)below;
+    unsigned m = 0;
+    for (int w = 0; w < kNwWarps; w++) m = s.wmax[w] > m ? s.wmax[w] : m;
+    cl_set_shape(s, (int)fl, m);
+    if (m == 0xffffffffu) s.rounds = (unsigned)kRounds + 1u;
     s.need_reload = 0;
+    s.just_reloaded = 1;
+    s.S.stat_reloads++;
   }
   __syncthreads();
 }
 
-// One BFS level across the cluster.  Returns the number of newly reached vertices (cluster
-// total), or -1 when the level has to be done by the wide path (nothing modified then).
-// On return *next_maxdeg holds the maximum degree among the new vertices.
-//
-//   sweep 1   every warp walks the concatenated adjacency lists of its part of the share 32
-//             slots at a time (kClBatch rounds in flight), claims with atomicMin and appends
-//             the claims that were the minimum when they landed to its provisional list
-//   barrier 1 all claims of the level have landed
-//   sweep 2   every warp re-reads the marks of its provisional claims (a claim survived iff
-//             the mark still equals its key), fetches the winners' adjacency extents in the
-//             same round trip and marks them visited
-//   compaction into slot order, counts exchanged through distributed shared memory (barrier 2)
-//   ordering  slot order (peripheral) or per-parent (degree, id) order (CM), written to the
-//             global queue and -- unless the shares drifted apart -- kept as the next share
+// One BFS level across the cluster.  Returns
+//    1  level done: the shares hold the next frontier (not yet in the global queue)
+//    0  the frontier was empty: the BFS is complete, the queue is complete and visible
+//   -1  some share did not fit: claims taken back, frontier in the queue; re-split and repeat
+//   -2  an even split does not fit either: the level belongs to the WIDE regime
 template <typename I, typename N, bool CM>
-__device__ long long cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a, ClSmem<I> &s,
-                              I *queue, int &par, unsigned cur_maxdeg, unsigned *next_maxdeg) {
+__device__ __forceinline__ int cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a,
+                                        ClSmem<I> &s, I *queue, unsigned &lxstate) {
   const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
   const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
-  const int64_t f = s.S.lvl_end - s.S.lvl_begin;
-  // uniform feasibility checks (every CTA evaluates the same replicated numbers)
-  if (s.max_slots > (unsigned long long)cl_el<I>()) return -1;
-  if (CM && cur_maxdeg > (unsigned)kNwGroupCap) return -1;
-  // Claim keys grow from level to level (CM: queue position of the parent; peripheral: running
-  // expansion-slot number of the BFS), so a vertex reached earlier always holds a SMALLER mark
-  // than any later claim: visited vertices need no separate "visited" store, and barrier 2 has
-  // no global writes to wait for.
-  if (!CM && (unsigned long long)s.S.key_base + s.level_slots >= 0xfffffff0ull) return -1;
-  const unsigned kb = CM ? (unsigned)s.S.lvl_begin : (unsigned)s.S.key_base + s.sbase;
-  (void)f;
   const int fl = s.fl;
-  const long long fb = s.fb;
-  long long t0 = clock64(), t1;
+  const unsigned D = s.D, invD = s.invD, R = s.rounds;
+  const bool fits = R <= (unsigned)kRounds;
+  const unsigned total = fits ? (unsigned)fl * D : 0u;
+  // level << 32 | rank << 16 | position inside the share: grows with the queue position
+  const unsigned long long klevel =
+      ((unsigned long long)(s.S.depth + 1) << 32) | ((unsigned long long)rank << 16);
+  long long t0 = a.profile ? clock64() : 0, t1;
 #define SB_TICK(slot)                                   \
   do {                                                  \
-    t1 = clock64();                                     \
-    if (threadIdx.x == 0) s.S.cyc[slot] += t1 - t0;     \
-    t0 = t1;                                            \
+    if (a.profile) {                                    \
+      t1 = clock64();                                   \
+      if (threadIdx.x == 0) s.S.cyc[slot] += t1 - t0;   \
+      t0 = t1;                                          \
+    }                                                   \
   } while (0)
 
-  unsigned pbase = 0;  // my warp's provisional region
+  // ---- claims: slot p = i * D + j of the share; warp w owns slots [w * 32 R, (w + 1) * 32 R)
+  I v[kRounds];
+  unsigned valid = 0, prov = 0;
+  const unsigned wbase = wid * 32u * R + lane;
+  // claim key of round r: the position part is the parent's index in the share (CM) or the
+  // slot (peripheral); recomputed where needed instead of being kept in registers
+  auto key_of = [&](int r) -> unsigned long long {
+    const unsigned p = wbase + (unsigned)r * 32u;
+    const unsigned i = D == 1u ? p : __umulhi(p, invD);
+    return klevel | (unsigned long long)(CM ? i : p);
+  };
 #pragma unroll
-  for (int w = 0; w < kNwWarps; w++) pbase += (unsigned)w < wid ? s.wslot[w] : 0u;
-  unsigned pcount = 0;
-  unsigned goff = pbase;  // expansion-slot number (inside this CTA's share) of the group's slot 0
+  for (int r = 0; r < kRounds; r++) {
+    if ((unsigned)r < R) {
+      const unsigned p = wbase + (unsigned)r * 32u;
+      if (p < total) {
+        const unsigned i = D == 1u ? p : __umulhi(p, invD);
+        const unsigned j = p - i * D;
+        if (j < s.Fd[i]) {
+          valid |= 1u << r;
+          v[r] = a.adj[s.Fx[i] + (int64_t)j];
+        }
+      }
+    }
+  }
+  unsigned long long old[kRounds];
+#pragma unroll
+  for (int r = 0; r < kRounds; r++)
+    if ((valid >> r) & 1u) old[r] = atomicMin(&a.mark[v[r]], key_of(r));
+#pragma unroll
+  for (int r = 0; r < kRounds; r++) {
+    if (((valid >> r) & 1u) && old[r] > key_of(r)) {
+      prov |= 1u << r;  // the smallest claim so far: a candidate
+      // its adjacency extent is read right after the exchange: pull the line towards L2 now
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.xadj + v[r]));
+    }
+  }
   SB_TICK(0);
 
-  // ---- sweep 1: claims.  key orders (global frontier position[, adjacency index]) ----
-  const int vb = cl_part_begin(fl, wid), ve = cl_part_begin(fl, wid + 1);
-  for (int g = vb; g < ve; g += 32) {
-    const int i = g + (int)lane;
-    int64_t xs = 0;
-    unsigned d = 0;
-    if (i < ve) {
-      xs = s.Fx[i];
-      d = s.Fd[i];
-    }
-    const unsigned incl = warp_inclusive_scan(d);
-    const unsigned excl = incl - d;
-    const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
-    for (unsigned b0 = 0; b0 < tot; b0 += 32 * kClBatch) {
-      I v[kClBatch];
-      unsigned key[kClBatch], own[kClBatch], old[kClBatch];
-      bool valid[kClBatch];
+  // ---- exchange (= all claims have landed), then the recheck loads first of all ----
+  unsigned long long m[kRounds];
+  N xs[kRounds], xe[kRounds];
+  const LxSum x = cl_lx_exchange(s, C, rank, fits, lxstate, [&] {
 #pragma unroll
-      for (int u = 0; u < kClBatch; u++) {
-        const unsigned sl = b0 + u * 32 + lane;
-        unsigned lo = 0;  // number of lanes whose inclusive end <= sl  == owner lane
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-          const unsigned val = __shfl_sync(0xffffffffu, incl, (lo + step - 1) & 31);
-          if (val <= sl) lo += step;
-        }
-        const unsigned j = lo & 31;
-        const int64_t xs_j = __shfl_sync(0xffffffffu, xs, j);
-        const unsigned excl_j = __shfl_sync(0xffffffffu, excl, j);
-        valid[u] = sl < tot;
-        own[u] = (unsigned)g + j;
-        key[u] = CM ? kb + (unsigned)(fb + g + j) + 1u : kb + goff + sl + 1u;
-        if (valid[u]) v[u] = a.adj[xs_j + (int64_t)(sl - excl_j)];
-      }
-#pragma unroll
-      for (int u = 0; u < kClBatch; u++)
-        if (valid[u]) old[u] = atomicMin(&a.mark[v[u]], key[u]);
-#pragma unroll
-      for (int u = 0; u < kClBatch; u++) {
-        const bool prov = valid[u] && old[u] > key[u];
-        const unsigned bal = __ballot_sync(0xffffffffu, prov);
-        if (prov) {
-          const unsigned at = pbase + pcount + __popc(bal & lanemask_lt());
-          s.pv[at] = v[u];
-          s.pkey[at] = key[u];
-          s.pi[at] = own[u];
-        }
-        pcount += __popc(bal);
+    for (int r = 0; r < kRounds; r++) {
+      if ((prov >> r) & 1u) {
+        m[r] = __ldcg(&a.mark[v[r]]);
+        xs[r] = a.xadj[v[r]];
+        xe[r] = a.xadj[v[r] + 1];
       }
     }
-    goff += tot;
-  }
+  });
   SB_TICK(1);
-  cluster.sync();
-  SB_TICK(2);
-
-  // ---- sweep 2: which provisional claims survived?  (warp-local lists) ----
-  unsigned wins = 0, mymax = 0, mysum = 0;
-  for (unsigned k0 = 0; k0 < pcount; k0 += 32 * kClBatch) {
-    I v[kClBatch];
-    unsigned m[kClBatch];
-    N xs[kClBatch], xe[kClBatch];
+  if (x.nofit) {  // uniform: take the claims back, publish the frontier, let the caller decide
 #pragma unroll
-    for (int u = 0; u < kClBatch; u++) {
-      const unsigned k = k0 + u * 32 + lane;
-      if (k < pcount) {
-        v[u] = s.pv[pbase + k];
-        m[u] = __ldcg(&a.mark[v[u]]);
-        xs[u] = a.xadj[v[u]];
-        xe[u] = a.xadj[v[u] + 1];
-      }
+    for (int r = 0; r < kRounds; r++)
+      if ((prov >> r) & 1u) atomicExch(&a.mark[v[r]], kUnvisited);
+    if (!s.share_written)
+      for (int k = threadIdx.x; k < fl; k += kNwBlock) queue[s.S.lvl_begin + x.cbase + k] = s.Fv[k];
+    __syncthreads();
+    const int reloaded = s.just_reloaded;
+    if (threadIdx.x == 0) {
+      if (!s.share_written) s.S.lvl_end = s.S.lvl_begin + x.ctotal;
+      s.S.frontier_maxdeg = x.dmax;
+      s.share_written = 1;
     }
+    cl_sync(cluster, C);
+    return reloaded ? -2 : -1;
+  }
+  if (!s.share_written)
+    for (int k = threadIdx.x; k < fl; k += kNwBlock) queue[s.S.lvl_begin + x.cbase + k] = s.Fv[k];
+  if (x.ctotal == 0u) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s.S.lvl_end = s.S.lvl_begin;
+      s.share_written = 1;
+    }
+    cl_sync(cluster, C);  // every CTA's queue writes of the last levels are visible
+    return 0;
+  }
+
+  // ---- winners, in slot order inside the warp ----
+  unsigned win = 0, run = 0, wmaxd = 0;
 #pragma unroll
-    for (int u = 0; u < kClBatch; u++) {
-      const unsigned k = k0 + u * 32 + lane;
-      if (k < pcount) {
-        if (m[u] == s.pkey[pbase + k]) {
-          const unsigned dg = (unsigned)(xe[u] - xs[u]);
-          // the winner is expanded in the next level, after two cluster barriers and the
-          // ordering: pull its adjacency into L2 meanwhile (the lists are read once per
-          // traversal, so the expansion would otherwise wait for HBM)
-          if (dg > 0) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + xs[u]));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + xe[u] - 1));
-          }
-          s.px[pbase + k] = (int64_t)xs[u];
-          s.pd[pbase + k] = dg;
-          mymax = dg > mymax ? dg : mymax;
-          mysum += dg;
-          wins++;
-        } else {
-          s.pkey[pbase + k] = 0u;
-        }
+  for (int r = 0; r < kRounds; r++) {
+    if ((unsigned)r < R) {
+      const bool w = ((prov >> r) & 1u) && m[r] == key_of(r);
+      if (w) {
+        win |= 1u << r;
+        const unsigned dg = (unsigned)(xe[r] - xs[r]);
+        wmaxd = dg > wmaxd ? dg : wmaxd;
       }
+      run += __popc(__ballot_sync(0xffffffffu, w));
     }
   }
-  wins = warp_reduce_sum(wins);
-  mymax = warp_reduce_max(mymax);
-  mysum = warp_reduce_sum(mysum);
+  wmaxd = __reduce_max_sync(0xffffffffu, wmaxd);
   if (lane == 0) {
-    s.wwin[wid] = wins;
-    s.wmax[wid] = mymax;
-    s.wsum[wid] = mysum;
+    s.wwin[wid] = run;
+    s.wmax[wid] = wmaxd;
+  }
+  SB_TICK(2);
+  __syncthreads();  // the share has been read by everybody (claims, queue write)
+  // lane w holds warp w's totals
+  const unsigned cw = lane < (unsigned)kNwWarps ? s.wwin[lane] : 0u;
+  const unsigned mw = lane < (unsigned)kNwWarps ? s.wmax[lane] : 0u;
+  unsigned wb = __reduce_add_sync(0xffffffffu, lane < wid ? cw : 0u);
+  const unsigned c = __reduce_add_sync(0xffffffffu, cw);
+  const unsigned dmax = __reduce_max_sync(0xffffffffu, mw);
+#pragma unroll
+  for (int r = 0; r < kRounds; r++) {
+    if ((unsigned)r < R) {
+      const bool w = (win >> r) & 1u;
+      const unsigned bal = __ballot_sync(0xffffffffu, w);
+      if (w) {
+        const unsigned at = wb + __popc(bal & lanemask_lt());
+        const unsigned dg = (unsigned)(xe[r] - xs[r]);
+        if (CM) {
+          s.Sv[at] = v[r];
+          s.Sp[at] = (unsigned)key_of(r) & 0xffffu;
+          s.Sx[at] = (int64_t)xs[r];
+          s.Sd[at] = dg;
+        } else {
+          s.Fv[at] = v[r];
+          s.Fx[at] = (int64_t)xs[r];
+          s.Fd[at] = dg;
+        }
+        // the winner is expanded in the next level: pull its adjacency towards L2 meanwhile
+        // (the lists are read once per traversal, so the expansion would otherwise wait for HBM)
+        if (dg > 0u) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + xs[r]));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + xe[r] - 1));
+        }
+      }
+      wb += __popc(bal);
+    }
   }
   SB_TICK(3);
-  __syncthreads();
-  // ---- ordered compaction of the winners (warp regions are already in slot order) ----
-  unsigned wb = 0, c_local = 0;
-#pragma unroll
-  for (int w = 0; w < kNwWarps; w++) {
-    const unsigned cw = s.wwin[w];
-    wb += (unsigned)w < wid ? cw : 0u;
-    c_local += cw;
-  }
-  for (unsigned k0 = 0; k0 < pcount; k0 += 32) {
-    const unsigned k = k0 + lane;
-    const bool win = k < pcount && s.pkey[pbase + k] != 0u;
-    const unsigned bal = __ballot_sync(0xffffffffu, win);
-    if (win) {
-      const unsigned at = wb + __popc(bal & lanemask_lt());
-      s.cv[at] = s.pv[pbase + k];
-      s.ci[at] = s.pi[pbase + k];
-      s.cx[at] = s.px[pbase + k];
-      s.cd[at] = s.pd[pbase + k];
-    }
-    wb += __popc(bal);
-  }
-  if (threadIdx.x == 0) {
-    unsigned mx = 0, sm = 0;
-#pragma unroll
-    for (int w = 0; w < kNwWarps; w++) {
-      mx = s.wmax[w] > mx ? s.wmax[w] : mx;
-      sm += s.wsum[w];
-    }
-    s.mine[0] = c_local;
-    s.mine[1] = mx;
-    s.mine[2] = sm;
-    s.mine[3] = 0;
-  }
-  SB_TICK(4);
-  cl_exchange(cluster, s, par);
-  const int c = (int)c_local;
-  // every warp reduces the C records with its first C lanes
-  unsigned ck = 0, mk = 0, sk = 0;
-  if (lane < C) {
-    ck = (unsigned)s.xch[par ^ 1][lane][0];
-    mk = (unsigned)s.xch[par ^ 1][lane][1];
-    sk = (unsigned)s.xch[par ^ 1][lane][2];
-  }
-  const long long cbase = warp_reduce_sum(lane < rank ? ck : 0u);
-  const long long ctotal = warp_reduce_sum(ck);
-  const long long cmax = warp_reduce_max(ck);
-  const unsigned nmax = warp_reduce_max(mk);
-  const unsigned long long smax = warp_reduce_max(sk);
-  const unsigned sbase_next = warp_reduce_sum(lane < rank ? sk : 0u);
-  const unsigned long long slots_next = warp_reduce_sum(sk);
-  *next_maxdeg = nmax;
-  // keep the shares where they are unless they have drifted too far apart (uniform decision)
-  const bool keep = cmax <= kFl && smax <= (unsigned long long)cl_el<I>() &&
-                    cmax <= 2 * ((ctotal + C - 1) / C) + 32;
-  SB_TICK(5);
-
-  // ---- next frontier: slot order (peripheral) or (parent, degree, id) order (CM); the
-  //      sibling groups of a parent never leave the CTA that owns the parent ----
-  const int64_t out0 = s.S.lvl_end + cbase;
-  for (int k = threadIdx.x; k < c; k += kNwBlock) {
-    int dst = k;
-    const I w = s.cv[k];
-    const unsigned dg = s.cd[k];
-    if (CM) {
-      const unsigned par_i = s.ci[k];
-      int rank_in = 0, left = 0;
-      for (int q = k - 1; q >= 0 && s.ci[q] == par_i; q--) {
-        left++;
-        rank_in += (s.cd[q] < dg || (s.cd[q] == dg && s.cv[q] < w)) ? 1 : 0;
+  // ---- replicated state for the next level, spread over the lanes of warp 0 (the other warps
+  //      are sorting meanwhile): every lane does one independent piece ----
+  if (wid == 0) {
+    if (lane == 0) {
+      if (dmax != D || (int)c != fl) cl_set_shape(s, (int)c, dmax);
+    } else if (lane == 1) {
+      s.S.prev_begin = s.S.lvl_begin;
+      s.S.lvl_begin += x.ctotal;
+      s.S.depth++;
+    } else if (lane == 2) {
+      s.S.stat_levels_narrow++;
+      s.share_written = 0;
+      s.just_reloaded = 0;
+      // the shares of the level just expanded: re-split when they have drifted apart (or when
+      // one of them nears the capacity an even split would stay well below)
+      const unsigned even = (x.ctotal + C - 1u) / C, dd = x.dmax > 0u ? x.dmax : 1u;
+      if (C > 1u && (x.cmax > 2u * even + 32u ||
+                     ((unsigned long long)x.cmax * dd > (unsigned long long)kPadCap * 3 / 4 &&
+                      (unsigned long long)even * dd <= (unsigned long long)kPadCap / 2)))
+        s.need_reload = 1;
+    } else if (lane == 3 && a.max_cluster > 0) {
+      // cluster sizing on the running mean of the padded slots per level
+      const unsigned long long work = (unsigned long long)x.ctotal * (x.dmax > 0u ? x.dmax : 1u);
+      const unsigned long long acc =
+          s.work_acc == ~0ull ? work * 16ull : s.work_acc - s.work_acc / 16ull + work;
+      s.work_acc = acc;
+      const int since = ++s.since_resize;
+      if (since >= 32) {
+        const unsigned long long mean = acc / 16ull;
+        const bool grow = (int)C < a.max_cluster && mean > (unsigned long long)a.grow_above * C;
+        const bool shrink = C > 1u && mean < (unsigned long long)a.shrink_below * C;
+        if (grow || shrink) {
+          int want = 1;
+          while (want < a.max_cluster && (unsigned long long)want * a.target < mean) want <<= 1;
+          if (want != (int)C) s.want_resize = want;
+        }
       }
-      for (int q = k + 1; q < c && s.ci[q] == par_i; q++)
-        rank_in += (s.cd[q] < dg || (s.cd[q] == dg && s.cv[q] < w)) ? 1 : 0;
-      dst = k - left + rank_in;
     }
-    queue[out0 + dst] = w;
-    if (keep) {  // c <= kFl
-      s.F[dst] = w;
-      s.Fx[dst] = s.cx[k];
-      s.Fd[dst] = dg;
-    }
-    // the next level starts by reading this vertex's adjacency list: pull it towards L2 now
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + s.cx[k]));
   }
-  if (threadIdx.x == 0) {
-    if (!CM) s.S.key_base += (int64_t)s.level_slots;  // this level's slots are used up
-    if (keep) {
-      s.fl = c;
-      s.fb = cbase;
-      s.sbase = sbase_next;
-      s.max_slots = smax;
-      s.level_slots = slots_next;
-    } else {
-      s.need_reload = 1;
+  if (CM) {
+    __syncthreads();
+    // (parent, degree, id) order: the winners of one parent are adjacent in slot order and never
+    // leave the CTA that owns the parent; rank inside the sibling group by enumeration
+    for (int k = threadIdx.x; k < (int)c; k += kNwBlock) {
+      const unsigned par_i = s.Sp[k], dgk = s.Sd[k];
+      const I vk = s.Sv[k];
+      const int64_t xk = s.Sx[k];
+      const bool has_l = k > 0 && s.Sp[k - 1] == par_i;
+      const bool has_r = k + 1 < (int)c && s.Sp[k + 1] == par_i;
+      int dst = k;
+      if (has_l || has_r) {  // (an only child stays where it is)
+        int left = 0, before = 0;
+        for (int q0 = k - 1; has_l && q0 >= 0; q0 -= 4) {
+          int nm = 0;
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int q = q0 - u;
+            if (q >= 0 && s.Sp[q] == par_i) {
+              nm++;
+              before += (s.Sd[q] < dgk || (s.Sd[q] == dgk && s.Sv[q] < vk)) ? 1 : 0;
+            }
+          }
+          left += nm;
+          if (nm < 4) break;
+        }
+        for (int q0 = k + 1; has_r && q0 < (int)c; q0 += 4) {
+          int nm = 0;
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int q = q0 + u;
+            if (q < (int)c && s.Sp[q] == par_i) {
+              nm++;
+              before += (s.Sd[q] < dgk || (s.Sd[q] == dgk && s.Sv[q] < vk)) ? 1 : 0;
+            }
+          }
+          if (nm < 4) break;
+        }
+        dst = k - left + before;
+      }
+      s.Fv[dst] = vk;
+      s.Fx[dst] = xk;
+      s.Fd[dst] = dgk;
     }
   }
   __syncthreads();
-  SB_TICK(6);
-  if (keep) cl_count_slots(s, c);  // ends with a barrier
-  SB_TICK(7);
+  SB_TICK(4);
 #undef SB_TICK
-  return ctotal;
+  return 1;
 }
 
 // min over queue[b, e) of (degree << 32 | position - b); *ties = how many vertices of the slice
@@ -574,17 +676,22 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
   const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
   const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
   int par = 0;
-  unsigned cur_maxdeg = 0;  // max degree over the current frontier (replicated)
+  unsigned lxstate = 0;  // see cl_lx_exchange
   if (threadIdx.x == 0) {
     s.S = *a.state;
     s.S.status = ST_RUNNING;
-    s.fl = 0;
-    s.fb = 0;
-    s.max_slots = 0;
-    s.need_reload = 1;  // nothing is resident yet: the first level splits the queue
+    cl_set_shape(s, 0, 1);
+    s.need_reload = 1;    // nothing is resident yet: a level in progress re-splits the queue
+    s.share_written = 1;  // ... which holds the whole frontier (S.lvl_begin .. S.lvl_end)
+    s.just_reloaded = 0;
+    s.want_resize = 0;
+    s.since_resize = 0;
+    s.work_acc = ~0ull;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cl_smem_u32(&s.lxbar[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cl_smem_u32(&s.lxbar[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-  cur_maxdeg = (unsigned)s.S.frontier_maxdeg;
+  cl_sync(cluster, C);  // the barriers exist before any CTA sends to them
 
   for (;;) {
     const int phase = s.S.phase;  // replicated state: identical in every CTA
@@ -639,7 +746,7 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
             const int64_t pos = s.S.qwp + off++;
             a.Q[pos] = (I)i;
             a.inv[i] = (I)pos;  // singleton component: reversed slice == itself
-            atomicExch(&a.mark[i], 0u);
+            atomicExch(&a.mark[i], 0ull);
           }
         }
         if (threadIdx.x == 0) {
@@ -673,61 +780,75 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
       const bool cm = phase == PH_CM_INIT;
       const I r = (I)s.S.root;
       const int64_t at = cm ? s.S.qwp : 0;
+      const int64_t rxs = (int64_t)a.xadj[r];
+      const unsigned rd = (unsigned)((int64_t)a.xadj[r + 1] - rxs);
       if (rank == 0 && threadIdx.x == 0) {
         (cm ? a.Q : a.Qp)[at] = r;
-        atomicExch(&a.mark[r], 0u);
+        atomicExch(&a.mark[r], 0ull);
       }
-      cur_maxdeg = (unsigned)((int64_t)a.xadj[r + 1] - (int64_t)a.xadj[r]);
       if (threadIdx.x == 0) {
         if (cm) {
           s.S.qst = s.S.qwp;
         } else {
           s.S.rlevel = s.S.qlevel;
-          s.S.key_base = 0;
         }
         s.S.lvl_begin = at;
         s.S.lvl_end = at + 1;
         s.S.prev_begin = at;
         s.S.depth = 0;
+        s.S.frontier_maxdeg = rd;
         s.S.phase = cm ? PH_CM_LEVEL : PH_PBFS_LEVEL;
         s.S.stat_bfs++;
-        s.need_reload = 1;  // the reload's barrier publishes the root to every CTA
+        // the root is the whole frontier and lives in CTA 0's share
+        if (rank == 0) {
+          s.Fv[0] = r;
+          s.Fx[0] = rxs;
+          s.Fd[0] = rd;
+          cl_set_shape(s, 1, rd);
+        } else {
+          cl_set_shape(s, 0, 1);
+        }
+        s.share_written = 1;
+        s.need_reload = 0;
+        s.just_reloaded = 0;
       }
       __syncthreads();
       continue;
     }
 
     if (phase == PH_PBFS_LEVEL || phase == PH_CM_LEVEL) {
-      const int64_t f = s.S.lvl_end - s.S.lvl_begin;
-      if (f == 0) {
-        cluster.sync();  // the queue is complete: the END phases read other CTAs' slices
+      I *queue = phase == PH_PBFS_LEVEL ? a.Qp : a.Q;
+      if (a.force_wide) {  // (the frontier is always in the queue here)
+        if (threadIdx.x == 0) s.S.status = ST_NEED_WIDE;
+        break;
+      }
+      if (s.want_resize) {
+        if (!s.share_written) cl_flush_share(cluster, s, queue, lxstate);
+        cl_sync(cluster, C);
+        if (threadIdx.x == 0) {
+          s.S.status = ST_NEED_RESIZE;
+          s.S.resize_to = s.want_resize;
+          s.S.stat_resizes++;
+        }
+        break;
+      }
+      if (s.need_reload) cl_reload<I, N>(cluster, a, s, queue, lxstate);
+      const int r = phase == PH_PBFS_LEVEL ? cl_level<I, N, false>(cluster, a, s, queue, lxstate)
+                                           : cl_level<I, N, true>(cluster, a, s, queue, lxstate);
+      if (r == 1) continue;
+      if (r == 0) {
         if (threadIdx.x == 0) s.S.phase = phase == PH_PBFS_LEVEL ? PH_PBFS_END : PH_CM_END;
         __syncthreads();
         continue;
       }
-      long long c = -1;
-      unsigned next_maxdeg = 0;
-      if (!a.force_wide && s.need_reload)
-        cl_reload<I, N>(cluster, a, s, phase == PH_PBFS_LEVEL ? a.Qp : a.Q, par);
-      if (!a.force_wide)
-        c = phase == PH_PBFS_LEVEL
-                ? cl_level<I, N, false>(cluster, a, s, a.Qp, par, cur_maxdeg, &next_maxdeg)
-                : cl_level<I, N, true>(cluster, a, s, a.Q, par, cur_maxdeg, &next_maxdeg);
-      if (c < 0) {
+      if (r == -1) {
+        if (threadIdx.x == 0) s.need_reload = 1;
         __syncthreads();
-        if (threadIdx.x == 0) s.S.status = ST_NEED_WIDE;
-        break;
-      }
-      cur_maxdeg = next_maxdeg;
-      if (threadIdx.x == 0) {
-        s.S.prev_begin = s.S.lvl_begin;
-        s.S.lvl_begin = s.S.lvl_end;
-        s.S.lvl_end += c;
-        s.S.depth++;
-        s.S.stat_levels_narrow++;
+        continue;
       }
       __syncthreads();
-      continue;
+      if (threadIdx.x == 0) s.S.status = ST_NEED_WIDE;
+      break;
     }
 
     // ================================================================ peripheral(): BFS end
@@ -748,7 +869,7 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
         unsigned ties;
         const unsigned long long best =
             cl_last_level_min<I, N>(a, s, a.Qp, s.S.prev_begin, s.S.lvl_begin, &ties);
-        new_root = (int64_t)a.Qp[s.S.prev_begin + (int64_t)(best & 0xffffffffull)];
+        new_root = (int64_t)__ldcg(a.Qp + s.S.prev_begin + (int64_t)(best & 0xffffffffull));
         // The next BFS of peripheral() starts from new_root.  If its eccentricity does not
         // exceed qlevel, peripheral() returns new_root and the Cuthill-McKee BFS walks the same
         // component from the same root: both traversals have the same level SETS, so the CM
@@ -777,8 +898,8 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
       }
       for (int64_t k = (int64_t)rank * kNwBlock + threadIdx.x; k < visited;
            k += (int64_t)C * kNwBlock)
-        atomicExch(&a.mark[a.Qp[k]], kUnvisited);
-      cluster.sync();
+        atomicExch(&a.mark[__ldcg(a.Qp + k)], kUnvisited);
+      cl_sync(cluster, C);
       continue;
     }
 
@@ -810,7 +931,8 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
           unsigned ties;
           const unsigned long long best =
               cl_last_level_min<I, N>(a, s, a.Q, s.S.prev_begin, s.S.lvl_begin, &ties);
-          const int64_t new_root = (int64_t)a.Q[s.S.prev_begin + (int64_t)(best & 0xffffffffull)];
+          const int64_t new_root =
+              (int64_t)__ldcg(a.Q + s.S.prev_begin + (int64_t)(best & 0xffffffffull));
           __syncthreads();
           if (threadIdx.x == 0) {
             if (ties == 1) {
@@ -835,8 +957,8 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
           }
           for (int64_t k = qst + (int64_t)rank * kNwBlock + threadIdx.x; k < end;
                k += (int64_t)C * kNwBlock)
-            atomicExch(&a.mark[a.Q[k]], kUnvisited);
-          cluster.sync();
+            atomicExch(&a.mark[__ldcg(a.Q + k)], kUnvisited);
+          cl_sync(cluster, C);
           continue;
         }
         __syncthreads();
@@ -857,16 +979,14 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
       }
       for (int64_t k = qst + (int64_t)rank * kNwBlock + threadIdx.x; k < end;
            k += (int64_t)C * kNwBlock)
-        a.inv[a.Q[k]] = (I)(qst + (end - 1 - k));
-      cluster.sync();
+        a.inv[__ldcg(a.Q + k)] = (I)(qst + (end - 1 - k));
+      cl_sync(cluster, C);
       continue;
     }
   }
   __syncthreads();
-  if (rank == 0 && threadIdx.x == 0) {
-    s.S.frontier_maxdeg = cur_maxdeg;
-    *a.state = s.S;
-  }
+  if (rank == 0 && threadIdx.x == 0) *a.state = s.S;
+  cl_sync(cluster, C);  // no CTA leaves while a peer may still address its shared memory
 }
 
 // ------------------------------------------------------------------------------------
@@ -882,12 +1002,12 @@ struct FrontierDegFn {
   }
 };
 
-// sweep 1: claims.  key = expansion slot + 1 (peripheral) or parent position + 1 (CM)
+// sweep 1: claims.  key = level << 32 | expansion slot (peripheral) or parent position (CM)
 template <typename I, typename N, bool CM>
 __global__ void __launch_bounds__(256)
     rcm_wide_claim_kernel(const I *__restrict__ frontier, int64_t f, const int64_t *__restrict__ off,
                           const N *__restrict__ xadj, const I *__restrict__ adj,
-                          unsigned *__restrict__ mark) {
+                          unsigned long long *__restrict__ mark, unsigned long long klevel) {
   const unsigned lane = lane_id();
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -904,8 +1024,9 @@ __global__ void __launch_bounds__(256)
     warp_expand(xs, d, [&](unsigned sl, unsigned j, int64_t p, bool valid) {
       if (valid) {
         const I v = adj[p];
-        const unsigned key = CM ? (unsigned)(g + j) + 1u : (unsigned)(slot0 + sl) + 1u;
-        if (__ldcg(&mark[v]) != 0u) atomicMin(&mark[v], key);
+        const unsigned long long key =
+            klevel | (CM ? (unsigned long long)(g + j) : (unsigned long long)(slot0 + sl));
+        if (__ldcg(&mark[v]) > key) atomicMin(&mark[v], key);
       }
     });
   }
@@ -917,9 +1038,9 @@ template <typename I, typename N, bool CM>
 __global__ void __launch_bounds__(256)
     rcm_wide_collect_kernel(const I *__restrict__ frontier, int64_t f,
                             const int64_t *__restrict__ off, const N *__restrict__ xadj,
-                            const I *__restrict__ adj, const unsigned *__restrict__ mark,
-                            uint64_t *__restrict__ ckey, uint32_t *__restrict__ cval,
-                            unsigned long long *__restrict__ counter) {
+                            const I *__restrict__ adj, const unsigned long long *__restrict__ mark,
+                            unsigned long long klevel, uint64_t *__restrict__ ckey,
+                            uint32_t *__restrict__ cval, unsigned long long *__restrict__ counter) {
   // counter[0] = number of winners, counter[1] = max degree among them
   const unsigned lane = lane_id();
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -937,11 +1058,11 @@ __global__ void __launch_bounds__(256)
     warp_expand(xs, d, [&](unsigned sl, unsigned j, int64_t p, bool valid) {
       bool win = false;
       I v = 0;
-      unsigned key = 0;
+      unsigned long long pk = 0;  // position part of the key
       if (valid) {
         v = adj[p];
-        key = CM ? (unsigned)(g + j) + 1u : (unsigned)(slot0 + sl) + 1u;
-        win = __ldcg(&mark[v]) == key;
+        pk = CM ? (unsigned long long)(g + j) : (unsigned long long)(slot0 + sl);
+        win = __ldcg(&mark[v]) == (klevel | pk);
       }
       const unsigned bal = __ballot_sync(0xffffffffu, win);
       if (bal) {
@@ -951,7 +1072,7 @@ __global__ void __launch_bounds__(256)
         if (win) {
           const unsigned long long k = base + __popc(bal & lanemask_lt());
           const unsigned dg = (unsigned)(xadj[v + 1] - xadj[v]);
-          ckey[k] = CM ? (((uint64_t)(key - 1u) << 32) | (uint64_t)dg) : (uint64_t)(key - 1u);
+          ckey[k] = CM ? ((uint64_t)pk << 32) | (uint64_t)dg : (uint64_t)pk;
           cval[k] = (uint32_t)v;
           atomicMax(counter + 1, (unsigned long long)dg);
         }
@@ -962,18 +1083,14 @@ __global__ void __launch_bounds__(256)
 
 template <typename I>
 __global__ void rcm_wide_commit_kernel(const uint32_t *__restrict__ sorted, int64_t c,
-                                       I *__restrict__ queue_out, unsigned *__restrict__ mark) {
+                                       I *__restrict__ queue_out) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < c) {
-    const uint32_t v = sorted[k];
-    queue_out[k] = (I)v;
-    mark[v] = 0u;
-  }
+  if (k < c) queue_out[k] = (I)sorted[k];
 }
 
 template <typename I>
-__global__ void rcm_reset_kernel(const I *__restrict__ q, int64_t cnt, unsigned *__restrict__ mark,
-                                 unsigned value) {
+__global__ void rcm_reset_kernel(const I *__restrict__ q, int64_t cnt,
+                                 unsigned long long *__restrict__ mark, unsigned long long value) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < cnt) mark[q[k]] = value;
 }
@@ -1016,20 +1133,21 @@ void rcm_wide_level(Workspace &ws, const RcmArgs<I, N> &a, WideCtx<I, N> &w, Rcm
   const I *frontier = queue + S.lvl_begin;
   const int64_t f = S.lvl_end - S.lvl_begin;
   const int grid = device_info(ws.device()).sm_count * 8;
+  const unsigned long long klevel = (unsigned long long)(S.depth + 1) << 32;
   exclusive_scan<int64_t>(ws, FrontierDegFn<I, N>{frontier, a.xadj}, w.off, f);
   SB_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(unsigned long long), st));
   if (cm) {
     SB_LAUNCH((rcm_wide_claim_kernel<I, N, true>), grid, 256, 0, st, frontier, f,
-              (const int64_t *)w.off, a.xadj, a.adj, a.mark);
+              (const int64_t *)w.off, a.xadj, a.adj, a.mark, klevel);
     SB_LAUNCH((rcm_wide_collect_kernel<I, N, true>), grid, 256, 0, st, frontier, f,
-              (const int64_t *)w.off, a.xadj, a.adj, (const unsigned *)a.mark, w.k0, w.v0,
-              w.counter);
+              (const int64_t *)w.off, a.xadj, a.adj, (const unsigned long long *)a.mark, klevel,
+              w.k0, w.v0, w.counter);
   } else {
     SB_LAUNCH((rcm_wide_claim_kernel<I, N, false>), grid, 256, 0, st, frontier, f,
-              (const int64_t *)w.off, a.xadj, a.adj, a.mark);
+              (const int64_t *)w.off, a.xadj, a.adj, a.mark, klevel);
     SB_LAUNCH((rcm_wide_collect_kernel<I, N, false>), grid, 256, 0, st, frontier, f,
-              (const int64_t *)w.off, a.xadj, a.adj, (const unsigned *)a.mark, w.k0, w.v0,
-              w.counter);
+              (const int64_t *)w.off, a.xadj, a.adj, (const unsigned long long *)a.mark, klevel,
+              w.k0, w.v0, w.counter);
   }
   unsigned long long cnt2[2] = {0, 0};
   int64_t slots = 0;
@@ -1039,7 +1157,8 @@ void rcm_wide_level(Workspace &ws, const RcmArgs<I, N> &a, WideCtx<I, N> &w, Rcm
   const unsigned long long c = cnt2[0];
   S.frontier_maxdeg = (int64_t)cnt2[1];
   SB_REQUIRE(slots < 0xfffffffell, SB200_ERR_BAD_ARG,
-             "RCM level with %lld expansion slots exceeds the 32-bit claim key", (long long)slots);
+             "RCM level with %lld expansion slots exceeds the 32-bit claim position",
+             (long long)slots);
   if (c > 0) {
     const uint32_t *sorted_v;
     if (cm) {
@@ -1058,13 +1177,18 @@ void rcm_wide_level(Workspace &ws, const RcmArgs<I, N> &a, WideCtx<I, N> &w, Rcm
       sorted_v = w.v1;
     }
     SB_LAUNCH((rcm_wide_commit_kernel<I>), (unsigned)ceil_div((int64_t)c, 256), 256, 0, st,
-              sorted_v, (int64_t)c, queue + S.lvl_end, a.mark);
+              sorted_v, (int64_t)c, queue + S.lvl_end);
   }
   S.prev_begin = S.lvl_begin;
   S.lvl_begin = S.lvl_end;
   S.lvl_end += (int64_t)c;
   S.depth++;
   S.stat_levels_wide++;
+}
+
+static int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 template <typename I, typename N>
@@ -1077,17 +1201,15 @@ void rcm_impl(Workspace &ws, int64_t n, int64_t nnz, const N *xadj, const I *adj
   a.n = n;
   a.xadj = xadj;
   a.adj = adj;
-  a.mark = ws.alloc<unsigned>(n);
+  a.mark = ws.alloc<unsigned long long>(n);
   a.Q = ws.alloc<I>(n);
   a.Qp = ws.alloc<I>(n);
   a.inv = out_inv;
   a.state = ws.alloc<RcmState>(1);
   a.force_wide = force_wide;
-  {
-    const char *ns = getenv("SB200_RCM_NO_SPEC");
-    a.no_spec = ns && ns[0] == '1';
-  }
-  SB_CUDA(cudaMemsetAsync(a.mark, 0xff, n * sizeof(unsigned), st));
+  a.no_spec = env_int("SB200_RCM_NO_SPEC", 0) == 1;
+  a.profile = env_int("SB200_RCM_PROFILE", 0) == 1;
+  SB_CUDA(cudaMemsetAsync(a.mark, 0xff, n * sizeof(unsigned long long), st));
   RcmState S;
   memset(&S, 0, sizeof(S));
   S.phase = PH_FIND;
@@ -1131,52 +1253,85 @@ void rcm_impl(Workspace &ws, int64_t n, int64_t nnz, const N *xadj, const I *adj
   cfg.stream = st;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  int cluster = kClMax;
-  if (const char *cs = getenv("SB200_RCM_CLUSTER")) {  // tuning aid: 1, 2, 4, 8 or 16
-    const int want = atoi(cs);
-    if (want >= 1 && want <= kClMax && (want & (want - 1)) == 0) cluster = want;
-  }
-  for (; cluster >= 1; cluster >>= 1) {  // largest cluster the device can co-schedule
-    cfg.gridDim = dim3(cluster, 1, 1);
-    attr[0].val.clusterDim.x = cluster;
+  auto set_cluster = [&](int c) {
+    cfg.gridDim = dim3(c, 1, 1);
+    attr[0].val.clusterDim.x = c;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+  };
+  // largest cluster the device can co-schedule
+  int max_cluster = kClMax;
+  for (; max_cluster >= 1; max_cluster >>= 1) {
+    set_cluster(max_cluster);
     int nclusters = 0;
     cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
     if (e == cudaSuccess && nclusters >= 1) break;
     cudaGetLastError();
   }
-  SB_REQUIRE(cluster >= 1, SB200_ERR_CUDA, "cannot launch the RCM cluster kernel");
-  const int64_t narrow_cap = (int64_t)cluster * kFl;
+  SB_REQUIRE(max_cluster >= 1, SB200_ERR_CUDA, "cannot launch the RCM cluster kernel");
+  // SB200_RCM_CLUSTER=c pins the cluster size (tuning aid: 1, 2, 4, 8 or 16); otherwise the
+  // kernel asks to be resized from the running mean of the frontier width
+  int cluster = max_cluster;
+  bool pinned = false;
+  {
+    const int want = env_int("SB200_RCM_CLUSTER", 0);
+    if (want >= 1 && want <= max_cluster && (want & (want - 1)) == 0) {
+      cluster = want;
+      pinned = true;
+    }
+  }
+  a.max_cluster = pinned ? 0 : max_cluster;
+  a.grow_above = env_int("SB200_RCM_GROW", kPadCap / 2);
+  a.shrink_below = env_int("SB200_RCM_SHRINK", kPadCap / 16);
+  a.target = env_int("SB200_RCM_TARGET", kPadCap / 4);
+  if (!pinned) cluster = 1;  // a BFS starts with one vertex
+  // an even split of f vertices of degree <= d over c CTAs fits the narrow regime
+  auto fits_narrow = [&](int64_t f, int64_t d, int c) {
+    return (f / c + 1) * (d > 0 ? d : 1) <= (int64_t)kPadCap;
+  };
   for (;;) {
+    set_cluster(cluster);
     SB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     launch_counter()++;
     SB_CUDA(cudaMemcpyAsync(&S, a.state, sizeof(S), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
     if (S.status == ST_DONE) break;
     if (S.status == ST_NEED_WIDE) {
-      prepare_wide();
       const bool cm = S.phase == PH_CM_LEVEL;
-      {
-        // the cluster kernel leaves the (monotone) claim key in mark[] of every vertex it
-        // reached; the wide kernels use per-level keys and expect 0 = visited
-        const int64_t from = cm ? S.qst : 0, cnt = S.lvl_end - from;
-        if (cnt > 0)
-          SB_LAUNCH((rcm_reset_kernel<I>), (unsigned)ceil_div(cnt, 256), 256, 0, st,
-                    (const I *)(cm ? a.Q : a.Qp) + from, cnt, a.mark, 0u);
+      const int64_t f = S.lvl_end - S.lvl_begin;
+      // a larger cluster may hold the level that did not fit this one
+      int bigger = cluster;
+      while (!pinned && !force_wide && bigger < max_cluster &&
+             !fits_narrow(f, S.frontier_maxdeg, bigger))
+        bigger <<= 1;
+      if (!force_wide && bigger != cluster && fits_narrow(f, S.frontier_maxdeg, bigger)) {
+        cluster = bigger;
+      } else {
+        prepare_wide();
+        // keep going wide while the frontier is beyond the narrow capacity
+        const int cap_cluster = pinned ? cluster : max_cluster;
+        do {
+          rcm_wide_level<I, N>(ws, a, w, S, cm);
+        } while (S.lvl_end > S.lvl_begin &&
+                 (force_wide ||
+                  !fits_narrow(S.lvl_end - S.lvl_begin, S.frontier_maxdeg, cap_cluster)));
+        if (!pinned) cluster = cap_cluster;
       }
-      // keep going wide while the frontier is far beyond the narrow capacity
-      do {
-        rcm_wide_level<I, N>(ws, a, w, S, cm);
-      } while (S.lvl_end - S.lvl_begin > (force_wide ? 0 : narrow_cap));
+    } else if (S.status == ST_NEED_RESIZE) {
+      int c = (int)S.resize_to;
+      if (c < 1) c = 1;
+      if (c > max_cluster) c = max_cluster;
+      cluster = c;
     } else if (S.status == ST_NEED_RESET) {
       const int64_t from = S.reset_cm ? S.qst : 0, cnt = S.lvl_end - from;
       SB_LAUNCH((rcm_reset_kernel<I>), (unsigned)ceil_div(cnt, 256), 256, 0, st,
                 (const I *)(S.reset_cm ? a.Q : a.Qp) + from, cnt, a.mark, kUnvisited);
+      if (!pinned) cluster = 1;  // the next BFS starts from a single vertex
     } else if (S.status == ST_NEED_INVERT) {
       const int64_t cnt = S.lvl_end - S.qst;
       SB_LAUNCH((rcm_invert_kernel<I>), (unsigned)ceil_div(cnt, 256), 256, 0, st, (const I *)a.Q,
                 S.qst, S.lvl_end, a.inv);
+      if (!pinned) cluster = 1;
     } else {
       SB_REQUIRE(false, SB200_ERR_INTERNAL, "RCM state machine returned status %d in phase %d",
                  S.status, S.phase);
@@ -1202,8 +1357,7 @@ int sb200_rcm_reorder(int device, int64_t n, int64_t nnz, const void *row_ptr, c
                "bad argument");
     SB_REQUIRE(nnz == 0 || col, SB200_ERR_BAD_ARG, "col is null");
     Workspace ws(device, (cudaStream_t)stream);
-    const char *fw = getenv("SB200_RCM_FORCE_WIDE");
-    const int force_wide = fw && fw[0] == '1';
+    const int force_wide = env_int("SB200_RCM_FORCE_WIDE", 0) == 1;
     dispatch_inv(id_type, nnz_type, SB200_VOID, false, [&](auto I_, auto N_, auto) {
       using I = decltype(I_);
       using N = decltype(N_);
@@ -1214,13 +1368,21 @@ int sb200_rcm_reorder(int device, int64_t n, int64_t nnz, const void *row_ptr, c
 }
 
 // Diagnostics of the last sb200_rcm_reorder call on this thread:
-// out[0..3] = levels done by the persistent CTA, levels done wide, BFS count, components.
+// out[0..3] = levels done by the persistent cluster kernel, levels done wide, BFS count,
+// components; out[4..5] (sb200_rcm_last_stats6) = share re-splits, cluster resizes.
 int sb200_rcm_last_stats(int64_t *h_out4) {
   if (!h_out4) return SB200_ERR_BAD_ARG;
   h_out4[0] = g_last_rcm_stats.stat_levels_narrow;
   h_out4[1] = g_last_rcm_stats.stat_levels_wide;
   h_out4[2] = g_last_rcm_stats.stat_bfs;
   h_out4[3] = g_last_rcm_stats.stat_components;
+  return SB200_OK;
+}
+
+int sb200_rcm_last_resplits(int64_t *h_out2) {
+  if (!h_out2) return SB200_ERR_BAD_ARG;
+  h_out2[0] = g_last_rcm_stats.stat_reloads;
+  h_out2[1] = g_last_rcm_stats.stat_resizes;
   return SB200_OK;
 }
 
@@ -1233,8 +1395,9 @@ int sb200_rcm_last_speculation(int64_t *h_out3) {
   return SB200_OK;
 }
 
-// Cycle counters of the cluster kernel's level phases (CTA 0): load, claim, check, finalize,
-// write -- a profiling aid, not part of the reference-facing surface.
+// Cycle counters of the cluster kernel's level phases (CTA 0): claims, barrier, recheck,
+// compaction, sibling sort + state update -- a profiling aid, not part of the reference-facing
+// surface.
 int sb200_rcm_last_cycles(int64_t *h_out8) {
   if (!h_out8) return SB200_ERR_BAD_ARG;
   for (int i = 0; i < 8; i++) h_out8[i] = g_last_rcm_stats.cyc[i];

@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kSrBlock, MINB)
     permute_short_rows_kernel(const RowRec<N> *__restrict__ rec, const N *__restrict__ out_ptr,
                               const I *__restrict__ adj, const V *__restrict__ vals,
                               const I *__restrict__ col_order, int64_t n,
-                              I *__restrict__ out_col, V *__restrict__ out_vals) {
+                              I *__restrict__ out_col, V *__restrict__ out_vals, DupCtx dc) {
   using VR = typename std::conditional<has_val<V>, V, char>::type;
   __shared__ I stage_k[kSrBlock / 32][32 * kShortRow];
   __shared__ VR stage_v[kSrBlock / 32][has_val<V> ? 32 * kShortRow : 1];
@@ -474,6 +474,7 @@ __global__ void __launch_bounds__(kSrBlock, MINB)
   unsigned char *own = stage_own[wid];
   const int64_t nbatches = (n + 31) >> 5;
   const int64_t wstride = ((int64_t)gridDim.x * kSrBlock) >> 5;
+  bool unsorted = false;  // some row has an inversion in source order (csr.cc:99-116)
   for (int64_t bt = (((int64_t)blockIdx.x * kSrBlock) >> 5) + wid; bt < nbatches; bt += wstride) {
     const int64_t j = (bt << 5) + lane;
     N ob = 0, p = 0;
@@ -535,8 +536,8 @@ __global__ void __launch_bounds__(kSrBlock, MINB)
       if (sidx < total) {
         const I k = c[u];
         // unique column ids (every valid input): the rank is the number of smaller ids.  The
-        // loop also counts the ids <= k; more than one means duplicates, which take the
-        // reference's (col, val) order in the rare path below.
+        // loop also counts the ids <= k; more than one means duplicates: those are ranked in
+        // source order and the row is flagged for the reference's tie rule (DupCtx).
         unsigned lt = 0, le = 0;
 #pragma unroll
         for (int t = 0; t < kShortRow; t++) {
@@ -546,22 +547,14 @@ __global__ void __launch_bounds__(kSrBlock, MINB)
             le += kj <= k ? 1u : 0u;
           }
         }
+        // in source order the entry sits at sidx - ex_o; the row is non-decreasing iff every
+        // entry lies inside the range of its equals
+        const unsigned at = sidx - ex_o;
+        if (at < lt || at >= le) unsorted = true;
         unsigned rank = lt;
-        if (le - lt > 1u) {  // duplicate column ids: (col, val) order, then position (csr.cc:147)
-          rank = 0;
-          for (unsigned jj = ex_o; jj < ex_o + len_o; jj++) {
-            const I kj = sk[jj];
-            bool before = kj < k;
-            if (kj == k) {
-              if constexpr (has_val<V>) {
-                const V vj = sv[jj];
-                before = vj < cv[u] || (!(cv[u] < vj) && jj < sidx);
-              } else {
-                before = jj < sidx;
-              }
-            }
-            rank += before ? 1u : 0u;
-          }
+        if (le - lt > 1u) {
+          for (unsigned jj = ex_o; jj < sidx; jj++) rank += sk[jj] == k ? 1u : 0u;
+          if (rank == lt + 1u) dc.flag((bt << 5) + owner);
         }
         st_stream(out_col + ob0 + ex_o + rank, k);
         if constexpr (has_val<V>) st_stream(out_vals + ob0 + ex_o + rank, (V)cv[u]);
@@ -569,6 +562,7 @@ __global__ void __launch_bounds__(kSrBlock, MINB)
     }
     __syncwarp();
   }
+  dc.report_unsorted(unsorted);
 }
 
 // ---- matrices whose longest row has <= 64 entries (random graphs of moderate degree, banded
@@ -592,9 +586,10 @@ __global__ void __launch_bounds__((mr_block<I, V>()))
     permute_mid_rows_kernel(const RowRec<N> *__restrict__ rec, const N *__restrict__ out_ptr,
                             const I *__restrict__ adj, const V *__restrict__ vals,
                             const I *__restrict__ col_order, int64_t n, bool stream,
-                            I *__restrict__ out_col, V *__restrict__ out_vals) {
+                            I *__restrict__ out_col, V *__restrict__ out_vals, DupCtx dc) {
   using VR = typename std::conditional<has_val<V>, V, char>::type;
   constexpr int kMrBlock = mr_block<I, V>();
+  bool unsorted = false;  // some row has an inversion in source order (csr.cc:99-116)
   __shared__ I stage_k[kMrBlock / 32][kMrCap];
   __shared__ VR stage_v[kMrBlock / 32][has_val<V> ? kMrCap : 1];
   __shared__ unsigned char stage_own[kMrBlock / 32][kMrCap];
@@ -673,22 +668,12 @@ __global__ void __launch_bounds__((mr_block<I, V>()))
           lt += kj < k ? 1u : 0u;
           le += kj <= k ? 1u : 0u;
         }
+        const unsigned at = sidx - ex_o;  // see permute_short_rows_kernel
+        if (at < lt || at >= le) unsorted = true;
         unsigned rank = lt;
-        if (le - lt > 1u) {  // duplicate column ids: (col, val) order, then position (csr.cc:147)
-          rank = 0;
-          for (unsigned jj = ex_o; jj < ex_o + len_o; jj++) {
-            const I kj = sk[jj];
-            bool before = kj < k;
-            if (kj == k) {
-              if constexpr (has_val<V>) {
-                const V vj = sv[jj], vm = sv[sidx];
-                before = vj < vm || (!(vm < vj) && jj < sidx);
-              } else {
-                before = jj < sidx;
-              }
-            }
-            rank += before ? 1u : 0u;
-          }
+        if (le - lt > 1u) {  // duplicate ids: source order here, the tie rule in dup_fix_kernel
+          for (unsigned jj = ex_o; jj < sidx; jj++) rank += sk[jj] == k ? 1u : 0u;
+          if (rank == lt + 1u) dc.flag(bt * R + owner);
         }
         st_stream(out_col + ob0 + ex_o + rank, k);
         if constexpr (has_val<V>) st_stream(out_vals + ob0 + ex_o + rank, (V)sv[sidx]);
@@ -696,12 +681,13 @@ __global__ void __launch_bounds__((mr_block<I, V>()))
     }
     __syncwarp();
   }
+  dc.report_unsorted(unsorted);
 }
 
 template <typename I, typename N, typename V>
 void permute2d_impl(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const N *xadj,
                     const I *adj, const V *vals, const I *row_order, const I *col_order,
-                    N *out_row_ptr, I *out_col, V *out_vals) {
+                    N *out_row_ptr, I *out_col, V *out_vals, int vkind) {
   cudaStream_t st = ws.stream();
   RowRec<N> *rec = ws.alloc<RowRec<N>>(n + 1);
   unsigned long long *max_len = ws.alloc<unsigned long long>(2);
@@ -718,6 +704,12 @@ void permute2d_impl(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const N *x
   SB_CUDA(cudaMemcpyAsync(h_stats, max_len, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   const unsigned long long h_max = h_stats[0];
+  // duplicate column ids (rare): flagged by the gather kernels, settled by dup_fix_kernel
+  DupCtx dc = {nullptr, nullptr, nullptr};
+  if constexpr (has_val<V>) {
+    if (h_max <= 64ull) dc = make_dup_ctx(ws, n, true);
+  }
+  GatherLoader<I, N, V> fix_ld{rec, adj, vals, col_order, false};
   if (h_max <= (unsigned long long)kShortRow) {
     // one 32-row batch per warp, CTAs in row order: neighbouring rows are in flight at the
     // same time, so the sectors they share (20-byte rows in 32-byte sectors, nearby col_order
@@ -733,11 +725,13 @@ void permute2d_impl(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const N *x
     if (minb == 5 || !narrow)
       SB_LAUNCH((permute_short_rows_kernel<I, N, V, 5>), grid, kSrBlock, 0, st,
                 (const RowRec<N> *)rec, (const N *)out_row_ptr, adj, vals, col_order, n, out_col,
-                out_vals);
+                out_vals, dc);
     else  // 40 registers: 48 resident warps per SM
       SB_LAUNCH((permute_short_rows_kernel<I, N, V, (narrow ? 6 : 5)>), grid, kSrBlock, 0, st,
                 (const RowRec<N> *)rec, (const N *)out_row_ptr, adj, vals, col_order, n, out_col,
-                out_vals);
+                out_vals, dc);
+    launch_dup_fix<I, N, V>(ws, fix_ld, (const N *)out_row_ptr, n, dc, false, out_col, out_vals,
+                            vkind);
     return;
   }
   static const int mid_env = [] {
@@ -756,17 +750,20 @@ void permute2d_impl(Workspace &ws, int64_t n, int64_t m, int64_t nnz, const N *x
       const unsigned grid = (unsigned)ceil_div(ceil_div(n, 16), kMrBlock / 32);
       SB_LAUNCH((permute_mid_rows_kernel<I, N, V, 16>), grid, kMrBlock, 0, st,
                 (const RowRec<N> *)rec, (const N *)out_row_ptr, adj, vals, col_order, n, stream,
-                out_col, out_vals);
+                out_col, out_vals, dc);
     } else {
       const unsigned grid = (unsigned)ceil_div(ceil_div(n, 8), kMrBlock / 32);
       SB_LAUNCH((permute_mid_rows_kernel<I, N, V, 8>), grid, kMrBlock, 0, st,
                 (const RowRec<N> *)rec, (const N *)out_row_ptr, adj, vals, col_order, n, stream,
-                out_col, out_vals);
+                out_col, out_vals, dc);
     }
+    launch_dup_fix<I, N, V>(ws, fix_ld, (const N *)out_row_ptr, n, dc, false, out_col, out_vals,
+                            vkind);
     return;
   }
   GatherLoader<I, N, V> ld{rec, adj, vals, col_order, stream};
-  segmented_sort<I, N, V>(ws, ld, (const N *)out_row_ptr, n, m, nnz, out_col, out_vals);
+  segmented_sort<I, N, V>(ws, ld, (const N *)out_row_ptr, n, m, nnz, out_col, out_vals, vkind,
+                          false);
 }
 
 // ---------------------------------------------------------------- row sharding
@@ -873,7 +870,7 @@ int sb200_permute2d(int device, int64_t n, int64_t m, int64_t nnz, const void *r
       using V = decltype(V_);
       permute2d_impl<I, N, V>(ws, n, m, nnz, (const N *)row_ptr, (const I *)col,
                               (const V *)vals, (const I *)row_order, (const I *)col_order,
-                              (N *)out_row_ptr, (I *)out_col, (V *)out_vals);
+                              (N *)out_row_ptr, (I *)out_col, (V *)out_vals, val_type);
     });
   });
 }

@@ -33,18 +33,37 @@ const DeviceInfo &device_info(int device) {
     infos[device].sm_count = p.multiProcessorCount;
     infos[device].max_smem_optin = (int)p.sharedMemPerBlockOptin;
     infos[device].l2_bytes = (int64_t)p.l2CacheSize;
-    // keep freed scratch blocks in the pool instead of returning them to the driver
-    cudaMemPool_t pool;
-    SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thresh = UINT64_MAX;
-    SB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     have[device] = true;
   }
   return infos[device];
 }
 
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pools[64] = {nullptr};
+
+cudaMemPool_t scratch_pool(int device) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  SB_REQUIRE(device >= 0 && device < 64, SB200_ERR_BAD_DEVICE, "device %d out of range", device);
+  if (!g_pools[device]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    cudaMemPool_t pool;
+    SB_CUDA(cudaMemPoolCreate(&pool, &props));
+    // keep freed scratch blocks in OUR pool instead of returning them to the driver on every
+    // stream synchronisation; sb200_trim gives them back
+    uint64_t thresh = UINT64_MAX;
+    SB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    g_pools[device] = pool;
+  }
+  return g_pools[device];
+}
+
 Workspace::Workspace(int device, cudaStream_t stream) : device_(device), stream_(stream) {
   device_info(device);
+  pool_ = scratch_pool(device);
 }
 Workspace::~Workspace() {
   for (void *p : ptrs_) cudaFreeAsync(p, stream_);
@@ -52,7 +71,7 @@ Workspace::~Workspace() {
 void *Workspace::alloc_bytes(size_t bytes) {
   void *p = nullptr;
   if (bytes == 0) bytes = 16;
-  cudaError_t e = cudaMallocAsync(&p, bytes, stream_);
+  cudaError_t e = cudaMallocFromPoolAsync(&p, bytes, pool_, stream_);
   if (e != cudaSuccess) {
     set_error("scratch allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
     throw Error{SB200_ERR_ALLOC};
@@ -171,6 +190,16 @@ int sb200_memcpy_d2d(int dst_device, void *dst, int src_device, const void *src,
       SB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     else
       SB_CUDA(cudaMemcpyPeerAsync(dst, dst_device, src, src_device, bytes, (cudaStream_t)stream));
+  });
+}
+
+int sb200_trim(int device) {
+  return guarded(device, [&] {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (device >= 0 && device < 64 && g_pools[device]) {
+      SB_CUDA(cudaDeviceSynchronize());
+      SB_CUDA(cudaMemPoolTrimTo(g_pools[device], 0));
+    }
   });
 }
 

@@ -13,9 +13,11 @@
 //   > kSsLong              : appended to a list; sorted afterwards by a segmented radix sort
 //                            on the index (radix_sort_segmented, see "long segments")
 //
-// Ties (duplicate indices inside a segment) are outside the parity contract; they
-// are ordered deterministically: original order (<=32 and >kSsLong: the sorts are stable) or
-// by the value (33..kSsLong).
+// Ties (duplicate indices inside a segment): the kernels here order them arbitrarily, flag the
+// segment (DupCtx, common.cuh) and report whether any segment was unsorted in source order;
+// dup_fix_kernel then applies the reference's rule -- (index, value) order in every segment when
+// any segment was unsorted (std::less<pair<IDType, ValueType>>, csr.cc:147, values compared in
+// their real type), source order otherwise (csr.cc:99-118: nothing is sorted then).
 #pragma once
 #include "common.cuh"
 #include "radix_sort.cuh"
@@ -82,13 +84,18 @@ struct SsSmem {
   unsigned nmid;
 };
 
-template <typename I, typename V>
-__device__ __forceinline__ bool ss_less(I ka, V va, I kb, V vb) {
-  if (ka != kb) return ka < kb;
-  if constexpr (has_val<V>)
-    return va < vb;
-  else
-    return false;
+// segment that owns output position `pos` (the last r with ptr[r] <= pos; rare path only)
+template <typename N>
+__device__ int64_t ss_segment_of(const N *__restrict__ ptr, int64_t n_seg, int64_t pos) {
+  int64_t lo = 0, hi = n_seg;  // first r with ptr[r] > pos
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)ptr[mid] <= pos)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo - 1;
 }
 
 // Loader concept:  int64_t seg_base(int64_t seg)  source offset of the segment's first entry
@@ -102,9 +109,10 @@ __device__ __forceinline__ bool ss_less(I ka, V va, I kb, V vb) {
 // the mark, and the per-segment source offset / length sit in tables indexed by that position.
 template <typename I, typename N, typename V, typename Loader>
 __global__ void __launch_bounds__(kSsBlock)
-    ss_tile_kernel(Loader ld, const N *__restrict__ ptr, const SsTileRec *__restrict__ rec,
-                   I *__restrict__ out_idx, V *__restrict__ out_val,
-                   int64_t *__restrict__ long_list, unsigned *__restrict__ long_count) {
+    ss_tile_kernel(Loader ld, const N *__restrict__ ptr, int64_t n_seg,
+                   const SsTileRec *__restrict__ rec, I *__restrict__ out_idx,
+                   V *__restrict__ out_val, int64_t *__restrict__ long_list,
+                   unsigned *__restrict__ long_count, DupCtx dc) {
   extern __shared__ __align__(16) unsigned char ss_smem_raw[];
   SsSmem<I, N, V> &s = *reinterpret_cast<SsSmem<I, N, V> *>(ss_smem_raw);
   const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
@@ -205,16 +213,22 @@ __global__ void __launch_bounds__(kSsBlock)
   __syncthreads();
 
   // ---- short segments: rank by enumeration, write straight to the final position ----
+  bool unsorted = false;  // some segment has an inversion in source order (csr.cc:99-116)
   for (int q = threadIdx.x; q < count; q += kSsBlock) {
     const int sb = (int)s.mark[q] - 1;
     const int len = s.len[sb];
-    if (len > kSsEnum) continue;
+    if (len > kSsEnum) continue;  // (their warp checks and sorts them below)
     const I k = s.key[q];
-    int rank = 0;  // entries before q count when <=, entries after q when < (stable)
+    if (q > sb && s.key[q - 1] > k) unsorted = true;
+    int rank = 0, same = 0;  // entries before q count when <=, entries after q when < (stable)
 #pragma unroll 4
-    for (int j = sb; j < q; j++) rank += s.key[j] <= k ? 1 : 0;
+    for (int j = sb; j < q; j++) {
+      rank += s.key[j] <= k ? 1 : 0;
+      same += s.key[j] == k ? 1 : 0;
+    }
 #pragma unroll 4
     for (int j = q + 1; j < sb + len; j++) rank += s.key[j] < k ? 1 : 0;
+    if (same == 1 && dc.seg_flag) dc.flag(ss_segment_of<N>(ptr, n_seg, first + sb));
     // outputs are written once and never read here: streaming stores keep them from pushing
     // the renumbering table out of L2
     st_stream(out_idx + first + sb + rank, k);
@@ -226,6 +240,9 @@ __global__ void __launch_bounds__(kSsBlock)
   for (unsigned mi = wid; mi < nmid; mi += kSsBlock / 32) {
     const int sb = (int)s.mid[mi], len = s.len[sb];
     I *key = s.key + sb;
+    for (int x = lane + 1; x < len; x += 32)
+      if (key[x - 1] > key[x]) unsorted = true;
+    __syncwarp();
     int P = 64;
     while (P < len) P <<= 1;
     for (int k = 2; k <= P; k <<= 1) {
@@ -237,19 +254,14 @@ __global__ void __launch_bounds__(kSsBlock)
           const int b2 = flip ? (a2 ^ (k - 1)) : (a2 | j);
           if (b2 < len) {
             const I ka = key[a2], kb = key[b2];
-            if constexpr (has_val<V>) {
-              V *val = reinterpret_cast<V *>(s.val) + sb;
-              const V va = val[a2], vb = val[b2];
-              if (ss_less<I, V>(kb, vb, ka, va)) {
-                key[a2] = kb;
-                key[b2] = ka;
-                val[a2] = vb;
+            if (kb < ka) {
+              key[a2] = kb;
+              key[b2] = ka;
+              if constexpr (has_val<V>) {
+                V *val = reinterpret_cast<V *>(s.val) + sb;
+                const V va = val[a2];
+                val[a2] = val[b2];
                 val[b2] = va;
-              }
-            } else {
-              if (kb < ka) {
-                key[a2] = kb;
-                key[b2] = ka;
               }
             }
           }
@@ -257,9 +269,67 @@ __global__ void __launch_bounds__(kSsBlock)
         __syncwarp();
       }
     }
+    bool dup = false;
     for (int x = lane; x < len; x += 32) {
+      if (x + 1 < len && key[x] == key[x + 1]) dup = true;
       st_stream(out_idx + first + sb + x, key[x]);
       if constexpr (has_val<V>) st_stream(out_val + first + sb + x, reinterpret_cast<V *>(s.val)[sb + x]);
+    }
+    if (dc.seg_flag && __any_sync(0xffffffffu, dup) && lane == 0)
+      dc.flag(ss_segment_of<N>(ptr, n_seg, first + sb));
+  }
+  dc.report_unsorted(unsorted);
+}
+
+// ------------------------------------------------------------------ duplicate ids (rare)
+// Runs after the fast kernels when some segment was flagged (see DupCtx).  One warp per flagged
+// segment of the OUTPUT layout:
+//   the sort happens (some segment was unsorted in source order, or the caller checked before):
+//     inside every run of equal ids the values are put in ascending order of their real type
+//   nothing was unsorted: the reference leaves every segment as it was -> the segment is copied
+//     again from the source, in source order
+template <typename I, typename N, typename V, typename Loader>
+__global__ void __launch_bounds__(256)
+    dup_fix_kernel(Loader ld, const N *__restrict__ ptr, int64_t n_seg, DupCtx dc, int sort_known,
+                   I *__restrict__ out_idx, V *__restrict__ out_val, int vkind) {
+  if (*reinterpret_cast<volatile unsigned *>(dc.any_dup) == 0u) return;
+  const bool sorted =
+      sort_known || (dc.unsorted && *reinterpret_cast<volatile unsigned *>(dc.unsorted) != 0u);
+  const unsigned lane = lane_id();
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r0 = warp * 32; r0 < n_seg; r0 += nwarps * 32) {
+    // 32 flags per warp step, then the flagged segments one at a time
+    const unsigned flagged =
+        __ballot_sync(0xffffffffu, r0 + lane < n_seg && dc.seg_flag[r0 + lane] != 0);
+    for (unsigned rest = flagged; rest; rest &= rest - 1) {
+      const int64_t r = r0 + (__ffs(rest) - 1);
+      const int64_t b = (int64_t)ptr[r], e = (int64_t)ptr[r + 1];
+      if (sorted) {
+        for (int64_t p = b + lane; p + 1 < e; p += 32) {
+          const I k = out_idx[p];
+          if (out_idx[p + 1] != k || (p > b && out_idx[p - 1] == k)) continue;
+          int64_t end = p + 2;  // run [p, end) of equal ids: insertion sort of its values
+          while (end < e && out_idx[end] == k) end++;
+          for (int64_t x = p + 1; x < end; x++) {
+            const V vx = out_val[x];
+            const V kx = val_order_key<V>(vx, vkind);
+            int64_t y = x;
+            while (y > p && val_order_key<V>(out_val[y - 1], vkind) > kx) {
+              out_val[y] = out_val[y - 1];
+              y--;
+            }
+            out_val[y] = vx;
+          }
+        }
+      } else {
+        const int64_t src = ld.seg_base(r);
+        for (int64_t t = lane; t < e - b; t += 32) {
+          out_idx[b + t] = ld.map_key(ld.raw_key(src + t));
+          out_val[b + t] = ld.val(src + t);
+        }
+      }
+      __syncwarp();
     }
   }
 }
@@ -326,12 +396,13 @@ __global__ void __launch_bounds__(256)
                         const int64_t *__restrict__ offs, const RsSeg *__restrict__ seg,
                         const int *__restrict__ chunk_seg,
                         typename std::make_unsigned<I>::type *__restrict__ keys,
-                        V *__restrict__ vals) {
+                        V *__restrict__ vals, DupCtx dc) {
   using UI = typename std::make_unsigned<I>::type;
   const RsSeg g = seg[blockIdx.x];
   const int k = chunk_seg[blockIdx.x];
   const int64_t src0 = ld.seg_base(list[k]) + (g.begin - offs[k]);
   constexpr int kBatch = 4;
+  bool unsorted = false;
   for (int q0 = 0; q0 < g.count; q0 += 256 * kBatch) {
     I raw[kBatch];
 #pragma unroll
@@ -348,6 +419,19 @@ __global__ void __launch_bounds__(256)
       if (q < g.count) keys[g.begin + q] = (UI)ld.map_key(raw[u]);
     }
   }
+  if (dc.unsorted) {  // inversions in source order (the keys just written, re-read from L2)
+    __syncthreads();
+    for (int q = threadIdx.x; q < g.count; q += 256) {
+      const UI cur = __ldcg(keys + g.begin + q);
+      UI prev = cur;
+      if (q > 0)
+        prev = __ldcg(keys + g.begin + q - 1);
+      else if (g.begin > offs[k])  // the entry before this chunk belongs to another CTA
+        prev = (UI)ld.map_key(ld.raw_key(src0 - 1));
+      if (prev > cur) unsorted = true;
+    }
+  }
+  dc.report_unsorted(unsorted);
 }
 
 template <typename I, typename N, typename V>
@@ -357,24 +441,56 @@ __global__ void __launch_bounds__(256)
                          const int *__restrict__ chunk_seg,
                          const typename std::make_unsigned<I>::type *__restrict__ keys,
                          const V *__restrict__ vals, I *__restrict__ out_idx,
-                         V *__restrict__ out_val) {
+                         V *__restrict__ out_val, DupCtx dc) {
   const RsSeg g = seg[blockIdx.x];
   const int k = chunk_seg[blockIdx.x];
   const int64_t dst0 = (int64_t)ptr[list[k]] + (g.begin - offs[k]);
+  bool dup = false;
   for (int q = threadIdx.x; q < g.count; q += 256) {
-    st_stream(out_idx + dst0 + q, (I)ld_stream(keys + g.begin + q));
+    const auto key = ld_stream(keys + g.begin + q);
+    if (dc.seg_flag && g.begin + q > offs[k] && keys[g.begin + q - 1] == key) dup = true;
+    st_stream(out_idx + dst0 + q, (I)key);
     if constexpr (has_val<V>) st_stream(out_val + dst0 + q, ld_stream(vals + g.begin + q));
+  }
+  if (dc.seg_flag && __syncthreads_or(dup ? 1 : 0) && threadIdx.x == 0) dc.flag(list[k]);
+}
+
+// Scratch of the duplicate-id rule for n_seg segments (flags zeroed on the stream).
+// `detect_unsorted` = false when the caller already knows that the sort happens.
+inline DupCtx make_dup_ctx(Workspace &ws, int64_t n_seg, bool detect_unsorted) {
+  cudaStream_t st = ws.stream();
+  DupCtx dc;
+  dc.seg_flag = ws.alloc<unsigned char>(n_seg > 0 ? n_seg : 1);
+  unsigned *two = ws.alloc<unsigned>(2);
+  dc.any_dup = two;
+  dc.unsorted = detect_unsorted ? two + 1 : nullptr;
+  SB_CUDA(cudaMemsetAsync(dc.seg_flag, 0, n_seg > 0 ? n_seg : 1, st));
+  SB_CUDA(cudaMemsetAsync(two, 0, 2 * sizeof(unsigned), st));
+  return dc;
+}
+
+template <typename I, typename N, typename V, typename Loader>
+void launch_dup_fix(Workspace &ws, Loader ld, const N *ptr, int64_t n_seg, const DupCtx &dc,
+                    bool sort_known, I *out_idx, V *out_val, int vkind) {
+  if constexpr (has_val<V>) {
+    if (!dc.seg_flag || n_seg <= 0) return;
+    SB_LAUNCH((dup_fix_kernel<I, N, V, Loader>), device_info(ws.device()).sm_count * 2, 256, 0,
+              ws.stream(), ld, ptr, n_seg, dc, sort_known ? 1 : 0, out_idx, out_val, vkind);
   }
 }
 
 // Sorts every segment of the output layout `ptr` (n_seg+1 offsets, nnz entries), pulling the
 // entries through `ld`.  n_idx bounds the index values (for the long-segment key width).
 // Synchronises the stream once (to learn how many long segments there are).
+// sort_known: the caller established that some segment is unsorted (constructor check), so
+// every segment is (index, value)-sorted; otherwise that is detected on the way (Permute2D).
 template <typename I, typename N, typename V, typename Loader>
 void segmented_sort(Workspace &ws, Loader ld, const N *ptr, int64_t n_seg, int64_t n_idx,
-                    int64_t nnz, I *out_idx, V *out_val) {
+                    int64_t nnz, I *out_idx, V *out_val, int vkind, bool sort_known) {
   if (nnz <= 0 || n_seg <= 0) return;
   cudaStream_t st = ws.stream();
+  DupCtx dc = {nullptr, nullptr, nullptr};
+  if constexpr (has_val<V>) dc = make_dup_ctx(ws, n_seg, !sort_known);
   const int64_t ntiles = ceil_div(nnz, kSsTile);
   SsTileRec *tile_rec = ws.alloc<SsTileRec>(ntiles + 1);
   // every long segment is the last one of a distinct window
@@ -386,12 +502,15 @@ void segmented_sort(Workspace &ws, Loader ld, const N *ptr, int64_t n_seg, int64
   auto kern = ss_tile_kernel<I, N, V, Loader>;
   SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)sizeof(SsSmem<I, N, V>)));
-  SB_LAUNCH(kern, (unsigned)ntiles, kSsBlock, sizeof(SsSmem<I, N, V>), st, ld, ptr,
-            (const SsTileRec *)tile_rec, out_idx, out_val, long_list, long_count);
+  SB_LAUNCH(kern, (unsigned)ntiles, kSsBlock, sizeof(SsSmem<I, N, V>), st, ld, ptr, n_seg,
+            (const SsTileRec *)tile_rec, out_idx, out_val, long_list, long_count, dc);
   unsigned nlong = 0;
   SB_CUDA(cudaMemcpyAsync(&nlong, long_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
-  if (nlong == 0) return;
+  if (nlong == 0) {
+    launch_dup_fix<I, N, V, Loader>(ws, ld, ptr, n_seg, dc, sort_known, out_idx, out_val, vkind);
+    return;
+  }
 
   // ---- long segments: segmented radix sort on the index ----
   using UI = typename std::make_unsigned<I>::type;
@@ -424,12 +543,13 @@ void segmented_sort(Workspace &ws, Loader ld, const N *ptr, int64_t n_seg, int64
   }
   SB_LAUNCH((ss_long_fill_kernel<I, N, V, Loader>), (unsigned)nchunks, 256, 0, st, ld,
             (const int64_t *)long_list, (const int64_t *)offs, (const RsSeg *)seg,
-            (const int *)chunk_seg, kin, vin);
+            (const int *)chunk_seg, kin, vin, dc);
   radix_sort_segmented<UI, V, NoVal>(ws, {kin, vin, nullptr}, {ka, va, nullptr},
                                      {kb, vb, nullptr}, total, seg, nchunks, idx_bits);
   SB_LAUNCH((ss_long_store_kernel<I, N, V>), (unsigned)nchunks, 256, 0, st, ptr,
             (const int64_t *)long_list, (const int64_t *)offs, (const RsSeg *)seg,
-            (const int *)chunk_seg, (const UI *)ka, (const V *)va, out_idx, out_val);
+            (const int *)chunk_seg, (const UI *)ka, (const V *)va, out_idx, out_val, dc);
+  launch_dup_fix<I, N, V, Loader>(ws, ld, ptr, n_seg, dc, sort_known, out_idx, out_val, vkind);
 }
 
 }  // namespace sb200

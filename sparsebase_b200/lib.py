@@ -21,9 +21,10 @@ SYMBOLS = [
     "sb200_abi_version", "sb200_last_error", "sb200_device_count", "sb200_can_access_peer",
     "sb200_enable_peer_access", "sb200_malloc", "sb200_free", "sb200_malloc_host",
     "sb200_free_host", "sb200_memcpy_h2d", "sb200_memcpy_d2h", "sb200_memcpy_d2d",
-    "sb200_stream_synchronize", "sb200_coo_sort", "sb200_compressed_sort", "sb200_coo_to_csr",
+    "sb200_stream_synchronize", "sb200_trim", "sb200_coo_sort", "sb200_compressed_sort", "sb200_coo_to_csr",
     "sb200_csr_to_coo", "sb200_coo_to_csc", "sb200_csr_to_csc", "sb200_degree_reorder",
     "sb200_rcm_reorder", "sb200_rcm_last_stats", "sb200_rcm_last_cycles",
+    "sb200_rcm_last_resplits",
     "sb200_rcm_last_speculation", "sb200_permute2d", "sb200_permute1d",
     "sb200_inverse_permutation",
     "sb200_degrees", "sb200_degree_distribution", "sb200_partition_rows", "sb200_launch_count",
@@ -74,13 +75,20 @@ def _i64(x):
     return ctypes.c_int64(int(x))
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-
 def _dev(t):
     assert t.is_cuda, "sparsebase_b200 operates on CUDA tensors only (no CPU fallback)"
     return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _stream(t=None):
+    """torch's current stream OF THE DEVICE THE OPERANDS LIVE ON (not of the current device)."""
+    dev = torch.cuda.current_device() if t is None else _dev(t)
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def trim(device=None):
+    """Return the library's cached scratch blocks on `device` to the driver."""
+    _check(load().sb200_trim(torch.cuda.current_device() if device is None else int(device)))
 
 
 def _vt(vals):
@@ -107,7 +115,7 @@ def coo_sort_(n, m, row, col, vals=None):
     flag = ctypes.c_int(0)
     _check(load().sb200_coo_sort(_dev(row), _i64(n), _i64(m), _i64(row.numel()), _p(row), _p(col),
                                  _p(vals), _DT[row.dtype], _vt(vals), ctypes.byref(flag),
-                                 _stream()))
+                                 _stream(row)))
     return bool(flag.value)
 
 
@@ -116,7 +124,7 @@ def compressed_sort_(n_seg, n_idx, ptr, idx, vals=None):
     flag = ctypes.c_int(0)
     _check(load().sb200_compressed_sort(_dev(idx), _i64(n_seg), _i64(n_idx), _i64(idx.numel()),
                                         _p(ptr), _p(idx), _p(vals), _DT[idx.dtype],
-                                        _DT[ptr.dtype], _vt(vals), ctypes.byref(flag), _stream()))
+                                        _DT[ptr.dtype], _vt(vals), ctypes.byref(flag), _stream(idx)))
     return bool(flag.value)
 
 
@@ -128,7 +136,7 @@ def coo_to_csr(n, m, row, col, vals=None, nnz_dtype=torch.int32):
     ovals = None if vals is None else torch.empty_like(vals)
     _check(load().sb200_coo_to_csr(_dev(row), _i64(n), _i64(m), _i64(nnz), _p(row), _p(col),
                                    _p(vals), _p(row_ptr), _p(ocol), _p(ovals), _DT[row.dtype],
-                                   _DT[nnz_dtype], _vt(vals), _stream()))
+                                   _DT[nnz_dtype], _vt(vals), _stream(row)))
     return row_ptr, ocol, ovals
 
 
@@ -139,7 +147,7 @@ def csr_to_coo(n, m, row_ptr, col, vals=None):
     ovals = None if vals is None else torch.empty_like(vals)
     _check(load().sb200_csr_to_coo(_dev(col), _i64(n), _i64(m), _i64(nnz), _p(row_ptr), _p(col),
                                    _p(vals), _p(orow), _p(ocol), _p(ovals), _DT[col.dtype],
-                                   _DT[row_ptr.dtype], _vt(vals), _stream()))
+                                   _DT[row_ptr.dtype], _vt(vals), _stream(col)))
     return orow, ocol, ovals
 
 
@@ -150,7 +158,7 @@ def coo_to_csc(n, m, row, col, vals=None, nnz_dtype=torch.int32):
     ovals = None if vals is None else torch.empty_like(vals)
     _check(load().sb200_coo_to_csc(_dev(row), _i64(n), _i64(m), _i64(nnz), _p(row), _p(col),
                                    _p(vals), _p(col_ptr), _p(orow), _p(ovals), _DT[row.dtype],
-                                   _DT[nnz_dtype], _vt(vals), _stream()))
+                                   _DT[nnz_dtype], _vt(vals), _stream(row)))
     return col_ptr, orow, ovals
 
 
@@ -164,7 +172,7 @@ def csr_to_csc(n, m, row_ptr, col, vals=None, out=None):
         col_ptr, orow, ovals = out
     _check(load().sb200_csr_to_csc(_dev(col), _i64(n), _i64(m), _i64(nnz), _p(row_ptr), _p(col),
                                    _p(vals), _p(col_ptr), _p(orow), _p(ovals), _DT[col.dtype],
-                                   _DT[row_ptr.dtype], _vt(vals), _stream()))
+                                   _DT[row_ptr.dtype], _vt(vals), _stream(col)))
     return col_ptr, orow, ovals
 
 
@@ -173,14 +181,14 @@ def degree_reorder(n, row_ptr, ascending=True, id_dtype=torch.int32):
     inv = torch.empty(n, dtype=id_dtype, device=row_ptr.device)
     _check(load().sb200_degree_reorder(_dev(row_ptr), _i64(n), _p(row_ptr),
                                        ctypes.c_int(1 if ascending else 0), _p(inv),
-                                       _DT[id_dtype], _DT[row_ptr.dtype], _stream()))
+                                       _DT[id_dtype], _DT[row_ptr.dtype], _stream(row_ptr)))
     return inv
 
 
 def rcm_reorder(n, row_ptr, col):
     inv = torch.empty(n, dtype=col.dtype, device=col.device)
     _check(load().sb200_rcm_reorder(_dev(col), _i64(n), _i64(col.numel()), _p(row_ptr), _p(col),
-                                    _p(inv), _DT[col.dtype], _DT[row_ptr.dtype], _stream()))
+                                    _p(inv), _DT[col.dtype], _DT[row_ptr.dtype], _stream(col)))
     return inv
 
 
@@ -190,8 +198,11 @@ def rcm_last_stats():
     d = dict(zip(("levels_narrow", "levels_wide", "bfs", "components"), list(out)))
     cyc = (ctypes.c_int64 * 8)()
     _check(load().sb200_rcm_last_cycles(cyc))
-    d["phase_cycles"] = dict(zip(("seek", "claim", "barrier1", "recheck", "compact", "exchange",
-                                  "sort_write", "rescan"), list(cyc)))
+    d["phase_cycles"] = dict(zip(("claim", "barrier", "recheck", "compact", "sort_state"),
+                                 list(cyc)[:5]))
+    rs = (ctypes.c_int64 * 2)()
+    _check(load().sb200_rcm_last_resplits(rs))
+    d["resplits"], d["resizes"] = int(rs[0]), int(rs[1])
     spec = (ctypes.c_int64 * 3)()
     _check(load().sb200_rcm_last_speculation(spec))
     d["spec_confirmed"], d["spec_continued"], d["spec_replayed"] = (int(x) for x in spec)
@@ -210,21 +221,21 @@ def permute2d(n, m, row_ptr, col, vals, row_order, col_order, out=None):
     _check(load().sb200_permute2d(_dev(col), _i64(n), _i64(m), _i64(nnz), _p(row_ptr), _p(col),
                                   _p(vals), _p(row_order), _p(col_order), _p(orp), _p(ocol),
                                   _p(ovals), _DT[col.dtype], _DT[row_ptr.dtype], _vt(vals),
-                                  _stream()))
+                                  _stream(col)))
     return orp, ocol, ovals
 
 
 def permute1d(vals, order):
     out = torch.empty_like(vals)
     _check(load().sb200_permute1d(_dev(vals), _i64(vals.numel()), _p(vals), _p(order), _p(out),
-                                  _DT[order.dtype], _DT[vals.dtype], _stream()))
+                                  _DT[order.dtype], _DT[vals.dtype], _stream(vals)))
     return out
 
 
 def inverse_permutation(perm):
     out = torch.empty_like(perm)
     _check(load().sb200_inverse_permutation(_dev(perm), _i64(perm.numel()), _p(perm), _p(out),
-                                            _DT[perm.dtype], _stream()))
+                                            _DT[perm.dtype], _stream(perm)))
     return out
 
 
@@ -232,7 +243,7 @@ def inverse_permutation(perm):
 def degrees(n, row_ptr, id_dtype=torch.int32):
     out = torch.empty(n, dtype=id_dtype, device=row_ptr.device)
     _check(load().sb200_degrees(_dev(row_ptr), _i64(n), _p(row_ptr), _p(out), _DT[id_dtype],
-                                _DT[row_ptr.dtype], _stream()))
+                                _DT[row_ptr.dtype], _stream(row_ptr)))
     return out
 
 
@@ -240,14 +251,14 @@ def degree_distribution(n, nnz, row_ptr, feature_dtype=torch.float32):
     out = torch.empty(n, dtype=feature_dtype, device=row_ptr.device)
     _check(load().sb200_degree_distribution(_dev(row_ptr), _i64(n), _i64(nnz), _p(row_ptr),
                                             _p(out), _DT[row_ptr.dtype], _DT[feature_dtype],
-                                            _stream()))
+                                            _stream(row_ptr)))
     return out
 
 
 def partition_rows(n, nnz, row_ptr, parts):
     bounds = (ctypes.c_int64 * (parts + 1))()
     _check(load().sb200_partition_rows(_dev(row_ptr), _i64(n), _i64(nnz), _p(row_ptr),
-                                       _DT[row_ptr.dtype], ctypes.c_int(parts), bounds, _stream()))
+                                       _DT[row_ptr.dtype], ctypes.c_int(parts), bounds, _stream(row_ptr)))
     return list(bounds)
 
 
@@ -260,7 +271,7 @@ def coo_to_csr_block(row_lo, n_local, m, row, col, vals=None, nnz_dtype=torch.in
     _check(load().sb200_coo_to_csr_block(_dev(row), _i64(row_lo), _i64(n_local), _i64(m),
                                          _i64(nnz), _p(row), _p(col), _p(vals), _p(row_ptr),
                                          _p(ocol), _p(ovals), _DT[row.dtype], _DT[nnz_dtype],
-                                         _vt(vals), _stream()))
+                                         _vt(vals), _stream(row)))
     return row_ptr, ocol, ovals
 
 
@@ -272,35 +283,35 @@ def csr_to_csc_block(row_lo, n_local, m, row_ptr, col, vals=None):
     _check(load().sb200_csr_to_csc_block(_dev(col), _i64(row_lo), _i64(n_local), _i64(m),
                                          _i64(nnz), _p(row_ptr), _p(col), _p(vals), _p(col_ptr),
                                          _p(orow), _p(ovals), _DT[col.dtype], _DT[row_ptr.dtype],
-                                         _vt(vals), _stream()))
+                                         _vt(vals), _stream(col)))
     return col_ptr, orow, ovals
 
 
 def exclusive_scan(x):
     out = torch.empty(x.numel() + 1, dtype=x.dtype, device=x.device)
     _check(load().sb200_exclusive_scan(_dev(x), _i64(x.numel()), _p(x), _p(out), _DT[x.dtype],
-                                       _stream()))
+                                       _stream(x)))
     return out
 
 
 def rank_keys(keys, key_bound):
     out = torch.empty_like(keys)
     _check(load().sb200_rank_keys(_dev(keys), _i64(keys.numel()), _p(keys), _i64(key_bound),
-                                  _p(out), _DT[keys.dtype], _stream()))
+                                  _p(out), _DT[keys.dtype], _stream(keys)))
     return out
 
 
 def max_degree(n, row_ptr):
     out = ctypes.c_int64(0)
     _check(load().sb200_max_degree(_dev(row_ptr), _i64(n), _p(row_ptr), _DT[row_ptr.dtype],
-                                   ctypes.byref(out), _stream()))
+                                   ctypes.byref(out), _stream(row_ptr)))
     return out.value
 
 
 def degree_histogram(n, row_ptr, nbins):
     out = torch.empty(nbins, dtype=torch.int64, device=row_ptr.device)
     _check(load().sb200_degree_histogram(_dev(row_ptr), _i64(n), _p(row_ptr), _DT[row_ptr.dtype],
-                                         _i64(nbins), _p(out), _stream()))
+                                         _i64(nbins), _p(out), _stream(row_ptr)))
     return out
 
 
@@ -308,5 +319,5 @@ def degree_rank_combine(n, row_ptr, local_rank, offset, flip_from=-1):
     out = torch.empty_like(local_rank)
     _check(load().sb200_degree_rank_combine(_dev(row_ptr), _i64(n), _p(row_ptr), _p(local_rank),
                                             _p(offset), _i64(flip_from), _p(out),
-                                            _DT[local_rank.dtype], _DT[row_ptr.dtype], _stream()))
+                                            _DT[local_rank.dtype], _DT[row_ptr.dtype], _stream(row_ptr)))
     return out

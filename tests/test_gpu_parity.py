@@ -444,3 +444,66 @@ def test_rcm_speculative_peripheral(sb, orc, monkeypatch):
             st = sb.rcm_last_stats()
             assert st["spec_confirmed"] == st["spec_continued"] == st["spec_replayed"] == 0
     assert all(v > 0 for v in seen.values()), seen
+
+
+@pytest.mark.parametrize("cluster", ["1", "2", "4", "8", "16"])
+def test_rcm_pinned_cluster_sizes(sb, orc, monkeypatch, cluster):
+    """Every cluster size of the narrow regime (single CTA with block barriers up to 16 CTAs with
+    one cluster barrier per level) yields the reference's permutation: grids (frontier grows and
+    shrinks), a shuffled band (constant narrow frontier, sibling groups of up to 31), several
+    components."""
+    monkeypatch.setenv("SB200_RCM_CLUSTER", cluster)
+    cases = []
+    n, rp, col, _ = graphs.poisson(301, 157)
+    cases.append((n, rp, col))
+    n, row, col = graphs.band(40000, 31, 0.5)
+    cases.append((n, graphs.csr_of(n, row, col), col))
+    n, row, col = graphs.multi_component()
+    cases.append((n, graphs.csr_of(n, row, col), col))
+    for n, rp, col in cases:
+        exp = orc.rcm_reorder(n, rp, col)
+        got = host(sb.rcm_reorder(n, dev(rp), dev(col)))
+        assert eq(got, exp), f"rcm mismatch at {np.flatnonzero(got != exp)[:10]}"
+        assert sb.rcm_last_stats()["resizes"] == 0
+
+
+def test_rcm_adaptive_cluster_and_resplit(sb, orc):
+    """Adaptive sizing: a wide grid makes the kernel ask for larger clusters as the frontier
+    grows and smaller ones as it shrinks, and the shares are re-split when they drift."""
+    n, rp, col, _ = graphs.poisson(2500, 900)
+    exp = orc.rcm_reorder(n, rp, col)
+    got = host(sb.rcm_reorder(n, dev(rp), dev(col)))
+    assert eq(got, exp), f"rcm mismatch at {np.flatnonzero(got != exp)[:10]}"
+    st = sb.rcm_last_stats()
+    assert st["levels_wide"] == 0 and st["resizes"] > 0 and st["resplits"] > 0, st
+
+
+def test_rcm_share_overflow_takes_claims_back(sb, orc, monkeypatch):
+    """A hub inside a narrow graph: the share holding it does not fit, the other CTAs take their
+    claims of that level back, the frontier is re-split and -- when even that does not fit --
+    the level is done by the wide regime; then the cluster resumes (rcm.cu cl_level abort)."""
+    nx, ny = 400, 60
+    n, rp, col, _ = graphs.poisson(nx, ny)
+    row = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+    rng = np.random.default_rng(5)
+    hubs = rng.choice(n, size=3, replace=False)
+    extra_r, extra_c = [], []
+    for h, deg in zip(hubs, (5000, 900, 70)):   # beyond one CTA, beyond a re-split, just wide rows
+        nb = rng.choice(n, size=deg, replace=False)
+        extra_r += [np.full(deg, h), nb]
+        extra_c += [nb, np.full(deg, h)]
+    rr = np.concatenate([row] + extra_r)
+    cc = np.concatenate([col.astype(np.int64)] + extra_c)
+    key = np.unique(rr * n + cc)
+    row2, col2 = (key // n).astype(np.int32), (key % n).astype(np.int32)
+    rp2 = graphs.csr_of(n, row2, col2)
+    exp = orc.rcm_reorder(n, rp2, col2)
+    for cluster in (None, "2", "16"):
+        if cluster is None:
+            monkeypatch.delenv("SB200_RCM_CLUSTER", raising=False)
+        else:
+            monkeypatch.setenv("SB200_RCM_CLUSTER", cluster)
+        got = host(sb.rcm_reorder(n, dev(rp2), dev(col2)))
+        assert eq(got, exp), f"rcm mismatch (cluster={cluster}) at {np.flatnonzero(got != exp)[:10]}"
+        st = sb.rcm_last_stats()
+        assert st["levels_narrow"] > 0 and st["levels_wide"] > 0, st
