@@ -18,6 +18,11 @@
  *   sb200_inverse_permutation bases/reorder_base.h:662-671     (ReorderBase::InversePermutation)
  *   sb200_degrees             feature/degrees.cc:93-105        (Degrees::GetDegreesCSR)
  *   sb200_degree_distribution feature/degree_distribution.cc:146-162 (GetDegreeDistributionCSR)
+ *   sb200_degree_features     feature/degrees_degree_distribution.cc:147-166 (fused degrees +
+ *                             distribution), feature/min_max_avg_degree.cc:168-191,
+ *                             feature/bandwidth.cc:92-111, feature/profile.cc:92-106
+ *   sb200_edges_to_coo        io/edge_list_reader.cc:28-151 (EdgeListReader::ReadCOO: self-edge
+ *                             removal, undirected expansion, (row,col) sort, unique)
  *   sb200_malloc/free/memcpy_*  converter/converter_order_two_cuda.cu:11-105,
  *                             converter/converter_order_one_cuda.cu:10-43, utils/utils_cuda.cuh:6-9
  *   sb200_can_access_peer     converter/converter_cuda.cu:12-21 (CUDAPeerToPeer)
@@ -189,6 +194,34 @@ int sb200_degrees(int device, int64_t n, const void *row_ptr, void *out_degrees,
 /* out_dist[i] = (row_ptr[i+1]-row_ptr[i]) / (FeatureType) nnz ; feature_type in {F32,F64} */
 int sb200_degree_distribution(int device, int64_t n, int64_t nnz, const void *row_ptr,
                               void *out_dist, int nnz_type, int feature_type, void *stream);
+
+/* Fused degree features and the quality metrics of a reordering: one pass over row_ptr
+ * (degrees, distribution, min / max degree) and one over col (bandwidth, profile).
+ * out_degrees (IDType[n]) and out_dist (FeatureType[n]) may be NULL; col may be NULL (then
+ * bandwidth = profile = 0).  h_out_scalars[4] (host) = {min_degree, max_degree,
+ * bandwidth = max |i-j| + 1 over the nonzeros, profile = sum_i (i - min(i, smallest column of
+ * row i))}; *h_out_avg (host, optional) = (row_ptr[n] - row_ptr[0]) / (FeatureType) n rounded
+ * in FeatureType.  Synchronises the stream. */
+int sb200_degree_features(int device, int64_t n, int64_t nnz, const void *row_ptr,
+                          const void *col, void *out_degrees, void *out_dist,
+                          int64_t *h_out_scalars, double *h_out_avg, int id_type, int nnz_type,
+                          int feature_type, void *stream);
+
+/* ---- edge list -> COO (the step before the COO constructor) ---- */
+
+/* EdgeListReader::ReadCOO on a device edge list u[n_edges], v[n_edges], w[n_edges] (w may be
+ * NULL): edges with u == v are dropped when remove_self_edges; with read_undirected the reverse
+ * edge follows every kept edge; n = max u + 1, m = max v + 1 over the kept edges, both set to
+ * the larger when square or read_undirected; the entries are sorted by (row, col) and, with
+ * remove_duplicates, the first entry of every run of equal (row, col) is kept -- the first in
+ * INPUT order (stable sort; the reference's std::sort leaves the survivor unspecified when
+ * duplicate edges carry different weights).  out_row / out_col / out_vals must hold
+ * n_edges * (read_undirected ? 2 : 1) entries; h_out3 (host) = {n, m, nnz}.
+ * Synchronises the stream. */
+int sb200_edges_to_coo(int device, int64_t n_edges, const void *u, const void *v, const void *w,
+                       int remove_duplicates, int remove_self_edges, int read_undirected,
+                       int square, void *out_row, void *out_col, void *out_vals,
+                       int64_t *h_out3, int id_type, int val_type, void *stream);
 
 /* ---- multi-GPU sharding helper ---- */
 

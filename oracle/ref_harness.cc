@@ -23,6 +23,12 @@
 //   ReorderBase::InversePermutation  src/sparsebase/bases/reorder_base.h:662-671
 //   Degrees / DegreeDistribution  src/sparsebase/feature/degrees.cc:93-105,
 //                                 src/sparsebase/feature/degree_distribution.cc:146-162
+//   Degrees_DegreeDistribution    src/sparsebase/feature/degrees_degree_distribution.cc:147-166
+//   MinDegree / MaxDegree / AvgDegree / Bandwidth / Profile
+//                                 src/sparsebase/feature/min_degree.cc, max_degree.cc:93-104,
+//                                 avg_degree.cc:128-137, bandwidth.cc:92-111, profile.cc:92-106
+//   EdgeListReader::ReadCOO       src/sparsebase/io/edge_list_reader.cc:28-151 (the edge list
+//                                 goes through a temporary text file: the reader is file based)
 //
 // Harness rules: the reference reads and writes mr[n], one element
 // past `new IDType[n]()`, in degree_reorder.cc:41-45 (heap overflow; it only "works" when the
@@ -44,18 +50,30 @@ void *operator new[](std::size_t sz) {
 void operator delete[](void *p) noexcept { std::free(p); }
 void operator delete[](void *p, std::size_t) noexcept { std::free(p); }
 
+#include <unistd.h>
+
+#include <any>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "sparsebase/bases/reorder_base.h"
 #include "sparsebase/context/cpu_context.h"
 #include "sparsebase/feature/degree_distribution.h"
+#include "sparsebase/feature/bandwidth.h"
 #include "sparsebase/feature/degrees.h"
+#include "sparsebase/feature/degrees_degree_distribution.h"
+#include "sparsebase/feature/avg_degree.h"
+#include "sparsebase/feature/max_degree.h"
+#include "sparsebase/feature/min_degree.h"
+#include "sparsebase/feature/profile.h"
 #include "sparsebase/format/array.h"
 #include "sparsebase/format/coo.h"
 #include "sparsebase/format/csc.h"
 #include "sparsebase/format/csr.h"
+#include "sparsebase/io/edge_list_reader.h"
 #include "sparsebase/reorder/degree_reorder.h"
 #include "sparsebase/reorder/rcm_reorder.h"
 #include "sparsebase/utils/logger.h"
@@ -234,6 +252,89 @@ int degree_distribution(int64_t n, int64_t m, N *row_ptr, I *col, V *vals, F *o_
   delete[] d;
   return 0;
 }
+
+// Fused degree features + the quality metrics of a reordering, through the reference's own
+// feature classes.  out_scalars = {min_degree, max_degree, bandwidth, profile}.
+template <typename I, typename N, typename V, typename F>
+int degree_features(int64_t n, int64_t m, N *row_ptr, I *col, I *o_deg, F *o_dist,
+                    int64_t *out_scalars, F *out_avg) {
+  format::CSR<I, N, V> csr((I)n, (I)m, row_ptr, col, (V *)nullptr, format::kNotOwned, true);
+  {
+    feature::Degrees_DegreeDistribution<I, N, V, F> f;
+    auto res = f.Get(&csr, {&g_cpu}, true);
+    I *d = std::any_cast<I *>(res[feature::Degrees<I, N, V>::get_id_static()]);
+    F *dist = std::any_cast<F *>(res[feature::DegreeDistribution<I, N, V, F>::get_id_static()]);
+    copy_out(o_deg, d, (size_t)n);
+    copy_out(o_dist, dist, (size_t)n);
+    delete[] d;
+    delete[] dist;
+  }
+  {
+    // (min_max_avg_degree.h and degrees_degree_distribution.h both define feature::Params and
+    // cannot share a translation unit: the three single features compute the same values,
+    // min_degree.cc / max_degree.cc / avg_degree.cc)
+    feature::MinDegree<I, N, V> fmin;
+    feature::MaxDegree<I, N, V> fmax;
+    feature::AvgDegree<I, N, V, F> favg;
+    N *mn = fmin.GetMinDegree(&csr, {&g_cpu}, true);
+    N *mx = fmax.GetMaxDegree(&csr, {&g_cpu}, true);
+    F *avg = favg.GetAvgDegree(&csr, {&g_cpu}, true);
+    out_scalars[0] = (int64_t)*mn;
+    out_scalars[1] = (int64_t)*mx;
+    if (out_avg) *out_avg = *avg;
+    delete mn;
+    delete mx;
+    delete avg;
+  }
+  {
+    feature::Bandwidth<I, N, V> f;
+    int *b = f.GetBandwidth(&csr, {&g_cpu}, true);
+    out_scalars[2] = (int64_t)*b;
+    delete b;
+  }
+  {
+    feature::Profile<I, N, V> f;
+    I *p = f.GetProfile(&csr, {&g_cpu}, true);
+    out_scalars[3] = (int64_t)*p;
+    delete p;
+  }
+  return 0;
+}
+
+template <typename I, typename N, typename V>
+int edges_to_coo(int64_t n_edges, I *u, I *v, V *w, int remove_duplicates, int remove_self,
+                 int undirected, int square, I *o_row, I *o_col, V *o_vals, int64_t *out3) {
+  char path[] = "/tmp/sbref_edges_XXXXXX";
+  int fd = mkstemp(path);
+  if (fd < 0) return 1;
+  FILE *fp = fdopen(fd, "w");
+  for (int64_t i = 0; i < n_edges; i++) {
+    if constexpr (std::is_same_v<V, void>) {
+      std::fprintf(fp, "%lld %lld\n", (long long)u[i], (long long)v[i]);
+    } else {
+      if (w)
+        std::fprintf(fp, "%lld %lld %.17g\n", (long long)u[i], (long long)v[i], (double)w[i]);
+      else
+        std::fprintf(fp, "%lld %lld\n", (long long)u[i], (long long)v[i]);
+    }
+  }
+  std::fclose(fp);
+  io::EdgeListReader<I, N, V> reader(std::string(path), w != nullptr, remove_duplicates != 0,
+                                     remove_self != 0, undirected != 0, square != 0);
+  auto *coo = reader.ReadCOO();
+  unlink(path);
+  const int64_t nnz = (int64_t)coo->get_num_nnz();
+  out3[0] = (int64_t)coo->get_dimensions()[0];
+  out3[1] = (int64_t)coo->get_dimensions()[1];
+  out3[2] = nnz;
+  copy_out(o_row, coo->get_row(), (size_t)nnz);
+  copy_out(o_col, coo->get_col(), (size_t)nnz);
+  if constexpr (!std::is_same_v<V, void>) {
+    if (w) copy_out(o_vals, coo->get_vals(), (size_t)nnz);
+  }
+  delete coo;
+  return 0;
+}
 }  // namespace
 
 // One block of extern "C" symbols per type triple.  TAG names IDType_NNZType_ValueType.
@@ -286,6 +387,16 @@ int degree_distribution(int64_t n, int64_t m, N *row_ptr, I *col, V *vals, F *o_
   int sbref_degree_distribution_##TAG(int64_t n, int64_t m, void *rp, void *col,             \
                                       void *vals, void *odist) {                             \
     return degree_distribution<I, N, V, F>(n, m, (N *)rp, (I *)col, (V *)vals, (F *)odist);  \
+  }                                                                                          \
+  int sbref_degree_features_##TAG(int64_t n, int64_t m, void *rp, void *col, void *odeg,     \
+                                  void *odist, int64_t *out4, void *oavg) {                  \
+    return degree_features<I, N, V, F>(n, m, (N *)rp, (I *)col, (I *)odeg, (F *)odist, out4, \
+                                       (F *)oavg);                                           \
+  }                                                                                          \
+  int sbref_edges_to_coo_##TAG(int64_t ne, void *u, void *v, void *w, int rd, int rs, int un,\
+                               int sq, void *orow, void *ocol, void *ovals, int64_t *out3) { \
+    return edges_to_coo<I, N, V>(ne, (I *)u, (I *)v, (V *)w, rd, rs, un, sq, (I *)orow,      \
+                                 (I *)ocol, (V *)ovals, out3);                               \
   }                                                                                          \
   }
 

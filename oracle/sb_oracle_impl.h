@@ -492,6 +492,118 @@ int FN(degree_distribution)(int64_t n, int64_t m, void *rp_, void *col_, void *v
   return 0;
 }
 
+/* feature/degrees_degree_distribution.cc:147-166 (fused degrees + distribution),
+ * feature/min_max_avg_degree.cc:168-191 (min / max over rows from rows[1]-rows[0], avg =
+ * degree_sum / (FeatureType) num_vertices), feature/bandwidth.cc:92-111 (max |i-j| + 1 over the
+ * nonzeros, an int), feature/profile.cc:92-106 (sum over rows of i - min(i, smallest column of
+ * the row); the reference accumulates it in IDType, here in int64_t -- identical while it fits).
+ * out_scalars = {min_degree, max_degree, bandwidth, profile}; *out_avg in FeatureType. */
+int FN(degree_features)(int64_t n, int64_t m, void *rp_, void *col_, void *odeg_, void *odist_,
+                        int64_t *out_scalars, void *out_avg_) {
+  const N *rows = (const N *)rp_;
+  const I *col = (const I *)col_;
+  I *deg = (I *)odeg_;
+  F *dist = (F *)odist_;
+  (void)m;
+  N num_edges = rows[n];
+  for (int64_t i = 0; i < n; i++) {
+    if (deg) deg[i] = (I)(rows[i + 1] - rows[i]);
+    if (dist) dist[i] = (rows[i + 1] - rows[i]) / (F)num_edges;
+  }
+  N mn = n > 0 ? rows[1] - rows[0] : 0, mx = mn;
+  for (int64_t i = 1; i < n; i++) {
+    N d = rows[i + 1] - rows[i];
+    if (d < mn) mn = d;
+    if (d > mx) mx = d;
+  }
+  int64_t bandwidth = 0, profile = 0;
+  if (col) {
+    for (int64_t i = 0; i < n; i++) {
+      int64_t j = i;
+      for (N k = rows[i]; k < rows[i + 1]; k++) {
+        int64_t c = (int64_t)col[k];
+        int64_t w = i >= c ? i - c + 1 : c - i + 1;
+        if (w > bandwidth) bandwidth = w;
+        if (j > c) j = c;
+      }
+      profile += i - j;
+    }
+  }
+  out_scalars[0] = (int64_t)mn;
+  out_scalars[1] = (int64_t)mx;
+  out_scalars[2] = bandwidth;
+  out_scalars[3] = profile;
+  if (out_avg_) *(F *)out_avg_ = n > 0 ? (rows[n] - rows[0]) / (F)n : (F)0;
+  return 0;
+}
+
+/* io/edge_list_reader.cc:28-151 -- EdgeListReader::ReadCOO on an in-memory edge list:
+ * self edges dropped when remove_self (:40 / :98), the reverse edge pushed right behind
+ * every kept edge when undirected (:43-44 / :101-102), n = max u + 1, m = max v + 1 over the
+ * kept edges (:46-47), squared when square || undirected (:51-54), sort by (row, col)
+ * (:56-65 / :114-123), unique on (row, col) keeping the first of each run (:67-75 / :125-134).
+ * The reference's std::sort is unstable: with duplicate edges of different weights, WHICH
+ * weight survives is unspecified there; this restatement (and the CUDA path) keep the first in
+ * input order.  Outputs must hold 2 * n_edges entries when undirected.
+ * out3 = {n, m, nnz}. */
+int FN(edges_to_coo)(int64_t n_edges, void *u_, void *v_, void *w_, int remove_duplicates,
+                     int remove_self, int undirected, int square, void *orow_, void *ocol_,
+                     void *ovals_, int64_t *out3) {
+  const I *u = (const I *)u_, *v = (const I *)v_;
+  const VT *w = (const VT *)w_;
+  I *orow = (I *)orow_, *ocol = (I *)ocol_;
+  VT *ovals = (VT *)ovals_;
+  (void)w;
+  (void)ovals;
+  size_t cap = (size_t)(n_edges > 0 ? n_edges : 1) * (undirected ? 2 : 1);
+  LOCAL(triple) *t = (LOCAL(triple) *)malloc(cap * sizeof(*t));
+  if (!t) return 1;
+  int64_t cnt = 0, n = 0, m = 0;
+  for (int64_t i = 0; i < n_edges; i++) {
+    if (u[i] != v[i] || !remove_self) {
+      t[cnt].row = u[i];
+      t[cnt].col = v[i];
+      t[cnt].idx = cnt;
+#if HAS_V
+      t[cnt].val = w ? w[i] : (VT)0;
+#endif
+      cnt++;
+      if (undirected) {
+        t[cnt].row = v[i];
+        t[cnt].col = u[i];
+        t[cnt].idx = cnt;
+#if HAS_V
+        t[cnt].val = w ? w[i] : (VT)0;
+#endif
+        cnt++;
+      }
+      if ((int64_t)u[i] + 1 > n) n = (int64_t)u[i] + 1;
+      if ((int64_t)v[i] + 1 > m) m = (int64_t)v[i] + 1;
+    }
+  }
+  if (square || undirected) {
+    if (m > n) n = m;
+    m = n;
+  }
+  qsort(t, (size_t)cnt, sizeof(*t), LOCAL(cmp_triple));
+  int64_t nnz = 0;
+  for (int64_t i = 0; i < cnt; i++) {
+    if (remove_duplicates && i > 0 && t[i].row == t[i - 1].row && t[i].col == t[i - 1].col)
+      continue;
+    orow[nnz] = t[i].row;
+    ocol[nnz] = t[i].col;
+#if HAS_V
+    if (ovals && w) ovals[nnz] = t[i].val;
+#endif
+    nnz++;
+  }
+  free(t);
+  out3[0] = n;
+  out3[1] = m;
+  out3[2] = nnz;
+  return 0;
+}
+
 #undef VT
 #undef FN
 #undef LOCAL

@@ -251,14 +251,14 @@ __device__ __forceinline__ unsigned cl_smem_u32(const void *p) {
 // lxstate: bit 0 = buffer / barrier to use, bits 1-2 = phase parity of the two barriers.
 template <typename I, typename Between>
 __device__ __forceinline__ LxSum cl_lx_exchange(ClSmem<I> &s, unsigned C, unsigned rank,
-                                                bool fits, unsigned &lxstate, Between &&between) {
-  const unsigned d = s.D > 0xffffffu ? 0xffffffu : s.D;
+                                                unsigned fl, unsigned D, bool fits,
+                                                unsigned &lxstate, Between &&between) {
+  const unsigned d = D > 0xffffffu ? 0xffffffu : D;
   // (share sizes never exceed kPadCap < 2^16)
-  const unsigned long long rec = (unsigned long long)(unsigned)s.fl |
-                                 ((unsigned long long)d << 16) | (fits ? 0ull : kLxNoFit);
+  const unsigned long long rec =
+      (unsigned long long)fl | ((unsigned long long)d << 16) | (fits ? 0ull : kLxNoFit);
   LxSum r = {0u, 0u, 0u, 0u, false};
   if (C == 1u) {  // nobody to talk to
-    const unsigned fl = (unsigned)s.fl;
     __syncthreads();
     between();
     r.ctotal = r.cmax = fl;
@@ -324,7 +324,7 @@ template <typename I>
 __device__ void cl_flush_share(cg::cluster_group &cluster, ClSmem<I> &s, I *queue,
                                unsigned &lxstate) {
   const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
-  const LxSum x = cl_lx_exchange(s, C, rank, true, lxstate, [] {});
+  const LxSum x = cl_lx_exchange(s, C, rank, (unsigned)s.fl, s.D, true, lxstate, [] {});
   for (int k = threadIdx.x; k < s.fl; k += kNwBlock) queue[s.S.lvl_begin + x.cbase + k] = s.Fv[k];
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -377,23 +377,26 @@ __device__ void cl_reload(cg::cluster_group &cluster, const RcmArgs<I, N> &a, Cl
   __syncthreads();
 }
 
-// One BFS level across the cluster.  Returns
-//    1  level done: the shares hold the next frontier (not yet in the global queue)
+// BFS levels across the cluster, until something other than "next level" has to happen.  The
+// level state (share shape, queue positions, depth, sizing statistics) lives in registers between
+// levels -- every thread computes the same replicated values from the exchanged records, so no
+// thread has a serial section -- and is stored back on the way out.  Returns
+//    1  stopped after a level because the shares want a re-split or the cluster a new size
 //    0  the frontier was empty: the BFS is complete, the queue is complete and visible
 //   -1  some share did not fit: claims taken back, frontier in the queue; re-split and repeat
 //   -2  an even split does not fit either: the level belongs to the WIDE regime
 template <typename I, typename N, bool CM>
-__device__ __forceinline__ int cl_level(cg::cluster_group &cluster, const RcmArgs<I, N> &a,
-                                        ClSmem<I> &s, I *queue, unsigned &lxstate) {
+__device__ __forceinline__ int cl_levels(cg::cluster_group &cluster, const RcmArgs<I, N> &a,
+                                         ClSmem<I> &s, I *queue, unsigned &lxstate) {
   const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
   const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
-  const int fl = s.fl;
-  const unsigned D = s.D, invD = s.invD, R = s.rounds;
-  const bool fits = R <= (unsigned)kRounds;
-  const unsigned total = fits ? (unsigned)fl * D : 0u;
-  // level << 32 | rank << 16 | position inside the share: grows with the queue position
-  const unsigned long long klevel =
-      ((unsigned long long)(s.S.depth + 1) << 32) | ((unsigned long long)rank << 16);
+  int fl = s.fl;
+  unsigned D = s.D, invD = s.invD, R = s.rounds;
+  int64_t lvl_begin = s.S.lvl_begin, prev_begin = s.S.prev_begin, lvl_end = s.S.lvl_end;
+  int64_t depth = s.S.depth, frontier_maxdeg = s.S.frontier_maxdeg;
+  bool written = s.share_written != 0, reloaded = s.just_reloaded != 0;
+  unsigned long long acc = s.work_acc;
+  int since = s.since_resize, nlevels = 0, need_reload = 0, want_resize = 0, ret;
   long long t0 = a.profile ? clock64() : 0, t1;
 #define SB_TICK(slot)                                   \
   do {                                                  \
@@ -404,231 +407,274 @@ __device__ __forceinline__ int cl_level(cg::cluster_group &cluster, const RcmArg
     }                                                   \
   } while (0)
 
-  // ---- claims: slot p = i * D + j of the share; warp w owns slots [w * 32 R, (w + 1) * 32 R)
-  I v[kRounds];
-  unsigned valid = 0, prov = 0;
-  const unsigned wbase = wid * 32u * R + lane;
-  // claim key of round r: the position part is the parent's index in the share (CM) or the
-  // slot (peripheral); recomputed where needed instead of being kept in registers
-  auto key_of = [&](int r) -> unsigned long long {
-    const unsigned p = wbase + (unsigned)r * 32u;
-    const unsigned i = D == 1u ? p : __umulhi(p, invD);
-    return klevel | (unsigned long long)(CM ? i : p);
-  };
-#pragma unroll
-  for (int r = 0; r < kRounds; r++) {
-    if ((unsigned)r < R) {
-      const unsigned p = wbase + (unsigned)r * 32u;
-      if (p < total) {
-        const unsigned i = D == 1u ? p : __umulhi(p, invD);
-        const unsigned j = p - i * D;
-        if (j < s.Fd[i]) {
-          valid |= 1u << r;
-          v[r] = a.adj[s.Fx[i] + (int64_t)j];
-        }
-      }
-    }
-  }
-  unsigned long long old[kRounds];
-#pragma unroll
-  for (int r = 0; r < kRounds; r++)
-    if ((valid >> r) & 1u) old[r] = atomicMin(&a.mark[v[r]], key_of(r));
-#pragma unroll
-  for (int r = 0; r < kRounds; r++) {
-    if (((valid >> r) & 1u) && old[r] > key_of(r)) {
-      prov |= 1u << r;  // the smallest claim so far: a candidate
-      // its adjacency extent is read right after the exchange: pull the line towards L2 now
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.xadj + v[r]));
-    }
-  }
-  SB_TICK(0);
+  for (;;) {
+    const bool fits = R <= (unsigned)kRounds;
+    const unsigned total = fits ? (unsigned)fl * D : 0u;
+    // level << 32 | rank << 16 | position inside the share: grows with the queue position
+    const unsigned long long klevel =
+        ((unsigned long long)(depth + 1) << 32) | ((unsigned long long)rank << 16);
 
-  // ---- exchange (= all claims have landed), then the recheck loads first of all ----
-  unsigned long long m[kRounds];
-  N xs[kRounds], xe[kRounds];
-  const LxSum x = cl_lx_exchange(s, C, rank, fits, lxstate, [&] {
+    // ---- claims: slot p = i * D + j of the share; warp w owns slots [w * 32 R, (w + 1) * 32 R)
+    I v[kRounds];
+    unsigned valid = 0, prov = 0;
+    const unsigned wbase = wid * 32u * R + lane;
+    // claim key of round r: the position part is the parent's index in the share (CM) or the
+    // slot (peripheral); recomputed where needed instead of being kept in registers
+    auto key_of = [&](int r) -> unsigned long long {
+      const unsigned p = wbase + (unsigned)r * 32u;
+      const unsigned i = D == 1u ? p : __umulhi(p, invD);
+      return klevel | (unsigned long long)(CM ? i : p);
+    };
 #pragma unroll
     for (int r = 0; r < kRounds; r++) {
-      if ((prov >> r) & 1u) {
-        m[r] = __ldcg(&a.mark[v[r]]);
-        xs[r] = a.xadj[v[r]];
-        xe[r] = a.xadj[v[r] + 1];
+      if ((unsigned)r < R) {
+        const unsigned p = wbase + (unsigned)r * 32u;
+        if (p < total) {
+          const unsigned i = D == 1u ? p : __umulhi(p, invD);
+          const unsigned j = p - i * D;
+          if (j < s.Fd[i]) {
+            valid |= 1u << r;
+            v[r] = a.adj[s.Fx[i] + (int64_t)j];
+          }
+        }
       }
     }
-  });
-  SB_TICK(1);
-  if (x.nofit) {  // uniform: take the claims back, publish the frontier, let the caller decide
+    unsigned long long old[kRounds];
 #pragma unroll
     for (int r = 0; r < kRounds; r++)
-      if ((prov >> r) & 1u) atomicExch(&a.mark[v[r]], kUnvisited);
-    if (!s.share_written)
-      for (int k = threadIdx.x; k < fl; k += kNwBlock) queue[s.S.lvl_begin + x.cbase + k] = s.Fv[k];
-    __syncthreads();
-    const int reloaded = s.just_reloaded;
-    if (threadIdx.x == 0) {
-      if (!s.share_written) s.S.lvl_end = s.S.lvl_begin + x.ctotal;
-      s.S.frontier_maxdeg = x.dmax;
-      s.share_written = 1;
+      if ((valid >> r) & 1u) old[r] = atomicMin(&a.mark[v[r]], key_of(r));
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) {
+      if (((valid >> r) & 1u) && old[r] > key_of(r)) {
+        prov |= 1u << r;  // the smallest claim so far: a candidate
+        // its adjacency extent is read right after the exchange: pull the line towards L2 now
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.xadj + v[r]));
+      }
     }
-    cl_sync(cluster, C);
-    return reloaded ? -2 : -1;
-  }
-  if (!s.share_written)
-    for (int k = threadIdx.x; k < fl; k += kNwBlock) queue[s.S.lvl_begin + x.cbase + k] = s.Fv[k];
-  if (x.ctotal == 0u) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      s.S.lvl_end = s.S.lvl_begin;
-      s.share_written = 1;
-    }
-    cl_sync(cluster, C);  // every CTA's queue writes of the last levels are visible
-    return 0;
-  }
+    SB_TICK(0);
 
-  // ---- winners, in slot order inside the warp ----
-  unsigned win = 0, run = 0, wmaxd = 0;
+    // ---- exchange (= all claims have landed), then the recheck loads first of all ----
+    unsigned long long m[kRounds];
+    N xs[kRounds], xe[kRounds];
+    const LxSum x = cl_lx_exchange(s, C, rank, (unsigned)fl, D, fits, lxstate, [&] {
 #pragma unroll
-  for (int r = 0; r < kRounds; r++) {
-    if ((unsigned)r < R) {
-      const bool w = ((prov >> r) & 1u) && m[r] == key_of(r);
-      if (w) {
-        win |= 1u << r;
-        const unsigned dg = (unsigned)(xe[r] - xs[r]);
-        wmaxd = dg > wmaxd ? dg : wmaxd;
-      }
-      run += __popc(__ballot_sync(0xffffffffu, w));
-    }
-  }
-  wmaxd = __reduce_max_sync(0xffffffffu, wmaxd);
-  if (lane == 0) {
-    s.wwin[wid] = run;
-    s.wmax[wid] = wmaxd;
-  }
-  SB_TICK(2);
-  __syncthreads();  // the share has been read by everybody (claims, queue write)
-  // lane w holds warp w's totals
-  const unsigned cw = lane < (unsigned)kNwWarps ? s.wwin[lane] : 0u;
-  const unsigned mw = lane < (unsigned)kNwWarps ? s.wmax[lane] : 0u;
-  unsigned wb = __reduce_add_sync(0xffffffffu, lane < wid ? cw : 0u);
-  const unsigned c = __reduce_add_sync(0xffffffffu, cw);
-  const unsigned dmax = __reduce_max_sync(0xffffffffu, mw);
-#pragma unroll
-  for (int r = 0; r < kRounds; r++) {
-    if ((unsigned)r < R) {
-      const bool w = (win >> r) & 1u;
-      const unsigned bal = __ballot_sync(0xffffffffu, w);
-      if (w) {
-        const unsigned at = wb + __popc(bal & lanemask_lt());
-        const unsigned dg = (unsigned)(xe[r] - xs[r]);
-        if (CM) {
-          s.Sv[at] = v[r];
-          s.Sp[at] = (unsigned)key_of(r) & 0xffffu;
-          s.Sx[at] = (int64_t)xs[r];
-          s.Sd[at] = dg;
-        } else {
-          s.Fv[at] = v[r];
-          s.Fx[at] = (int64_t)xs[r];
-          s.Fd[at] = dg;
-        }
-        // the winner is expanded in the next level: pull its adjacency towards L2 meanwhile
-        // (the lists are read once per traversal, so the expansion would otherwise wait for HBM)
-        if (dg > 0u) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + xs[r]));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + xe[r] - 1));
+      for (int r = 0; r < kRounds; r++) {
+        if ((prov >> r) & 1u) {
+          m[r] = __ldcg(&a.mark[v[r]]);
+          xs[r] = a.xadj[v[r]];
+          xe[r] = a.xadj[v[r] + 1];
         }
       }
-      wb += __popc(bal);
+    });
+    SB_TICK(1);
+    if (x.nofit) {  // uniform: take the claims back, publish the frontier, let the caller decide
+#pragma unroll
+      for (int r = 0; r < kRounds; r++)
+        if ((prov >> r) & 1u) atomicExch(&a.mark[v[r]], kUnvisited);
+      if (!written) {
+        for (int k = threadIdx.x; k < fl; k += kNwBlock) queue[lvl_begin + x.cbase + k] = s.Fv[k];
+        lvl_end = lvl_begin + x.ctotal;
+        written = true;
+      }
+      frontier_maxdeg = x.dmax;
+      cl_sync(cluster, C);
+      ret = reloaded ? -2 : -1;
+      break;
     }
-  }
-  SB_TICK(3);
-  // ---- replicated state for the next level, spread over the lanes of warp 0 (the other warps
-  //      are sorting meanwhile): every lane does one independent piece ----
-  if (wid == 0) {
+    if (!written)
+      for (int k = threadIdx.x; k < fl; k += kNwBlock) queue[lvl_begin + x.cbase + k] = s.Fv[k];
+    if (x.ctotal == 0u) {
+      lvl_end = lvl_begin;
+      written = true;
+      cl_sync(cluster, C);  // every CTA's queue writes of the last levels are visible
+      ret = 0;
+      break;
+    }
+
+    // ---- winners, in slot order inside the warp ----
+    unsigned win = 0, run = 0, wmaxd = 0;
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) {
+      if ((unsigned)r < R) {
+        const bool w = ((prov >> r) & 1u) && m[r] == key_of(r);
+        if (w) {
+          win |= 1u << r;
+          const unsigned dg = (unsigned)(xe[r] - xs[r]);
+          wmaxd = dg > wmaxd ? dg : wmaxd;
+        }
+        run += __popc(__ballot_sync(0xffffffffu, w));
+      }
+    }
+    wmaxd = __reduce_max_sync(0xffffffffu, wmaxd);
     if (lane == 0) {
-      if (dmax != D || (int)c != fl) cl_set_shape(s, (int)c, dmax);
-    } else if (lane == 1) {
-      s.S.prev_begin = s.S.lvl_begin;
-      s.S.lvl_begin += x.ctotal;
-      s.S.depth++;
-    } else if (lane == 2) {
-      s.S.stat_levels_narrow++;
-      s.share_written = 0;
-      s.just_reloaded = 0;
+      s.wwin[wid] = run;
+      s.wmax[wid] = wmaxd;
+    }
+    SB_TICK(2);
+    __syncthreads();  // the share has been read by everybody (claims, queue write)
+    // lane w holds warp w's totals
+    const unsigned cw = lane < (unsigned)kNwWarps ? s.wwin[lane] : 0u;
+    const unsigned mw = lane < (unsigned)kNwWarps ? s.wmax[lane] : 0u;
+    unsigned wb = __reduce_add_sync(0xffffffffu, lane < wid ? cw : 0u);
+    const unsigned c = __reduce_add_sync(0xffffffffu, cw);
+    const unsigned dmax = __reduce_max_sync(0xffffffffu, mw);
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) {
+      if ((unsigned)r < R) {
+        const bool w = (win >> r) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, w);
+        if (w) {
+          const unsigned at = wb + __popc(bal & lanemask_lt());
+          const unsigned dg = (unsigned)(xe[r] - xs[r]);
+          if (CM) {
+            s.Sv[at] = v[r];
+            s.Sp[at] = (unsigned)key_of(r) & 0xffffu;
+            s.Sx[at] = (int64_t)xs[r];
+            s.Sd[at] = dg;
+          } else {
+            s.Fv[at] = v[r];
+            s.Fx[at] = (int64_t)xs[r];
+            s.Fd[at] = dg;
+          }
+          // the winner is expanded in the next level: pull its adjacency towards L2 meanwhile
+          // (the lists are read once per traversal: the expansion would otherwise wait for HBM)
+          if (dg > 0u) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + xs[r]));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + xe[r] - 1));
+          }
+        }
+        wb += __popc(bal);
+      }
+    }
+    SB_TICK(3);
+    if (CM) {
+      __syncthreads();
+      // (parent, degree, id) order: the winners of one parent are adjacent in slot order and
+      // never leave the CTA that owns the parent; rank inside the sibling group by enumeration
+      if (D <= 8u) {  // small sibling groups: one thread per winner
+        for (int k = threadIdx.x; k < (int)c; k += kNwBlock) {
+          const unsigned par_i = s.Sp[k], dgk = s.Sd[k];
+          const I vk = s.Sv[k];
+          const int64_t xk = s.Sx[k];
+          int left = 0, before = 0;
+#pragma unroll
+          for (int u = 1; u < 8; u++) {  // a group has at most D <= 8 members
+            const int ql = k - u, qr = k + u;
+            if (ql >= 0 && s.Sp[ql] == par_i) {
+              left++;
+              before += (s.Sd[ql] < dgk || (s.Sd[ql] == dgk && s.Sv[ql] < vk)) ? 1 : 0;
+            }
+            if (qr < (int)c && s.Sp[qr] == par_i)
+              before += (s.Sd[qr] < dgk || (s.Sd[qr] == dgk && s.Sv[qr] < vk)) ? 1 : 0;
+          }
+          const int dst = k - left + before;
+          s.Fv[dst] = vk;
+          s.Fx[dst] = xk;
+          s.Fd[dst] = dgk;
+        }
+      } else {  // wide sibling groups (bands): one warp per winner, 32 siblings per step
+        for (int k = wid; k < (int)c; k += kNwWarps) {
+          const unsigned par_i = s.Sp[k], dgk = s.Sd[k];
+          const I vk = s.Sv[k];
+          int left = 0, before = 0;
+          for (int base = k - 1; base >= 0; base -= 32) {
+            const int q = base - (int)lane;
+            const bool mt = q >= 0 && s.Sp[q] == par_i;
+            const unsigned bal = __ballot_sync(0xffffffffu, mt);
+            const int cnt = bal == 0xffffffffu ? 32 : __ffs(~bal) - 1;  // matches are a prefix
+            const bool less = (int)lane < cnt &&
+                              (s.Sd[q] < dgk || (s.Sd[q] == dgk && s.Sv[q] < vk));
+            before += __popc(__ballot_sync(0xffffffffu, less));
+            left += cnt;
+            if (cnt < 32) break;
+          }
+          for (int base = k + 1; base < (int)c; base += 32) {
+            const int q = base + (int)lane;
+            const bool mt = q < (int)c && s.Sp[q] == par_i;
+            const unsigned bal = __ballot_sync(0xffffffffu, mt);
+            const int cnt = bal == 0xffffffffu ? 32 : __ffs(~bal) - 1;
+            const bool less = (int)lane < cnt &&
+                              (s.Sd[q] < dgk || (s.Sd[q] == dgk && s.Sv[q] < vk));
+            before += __popc(__ballot_sync(0xffffffffu, less));
+            if (cnt < 32) break;
+          }
+          if (lane == 0) {
+            const int dst = k - left + before;
+            s.Fv[dst] = vk;
+            s.Fx[dst] = s.Sx[k];
+            s.Fd[dst] = dgk;
+          }
+        }
+      }
+    }
+    // ---- the next level's state: the same arithmetic in every thread of every CTA ----
+    {
+      const unsigned nd = dmax > 0u ? dmax : 1u;
+      if (nd != D) {
+        D = nd;
+        invD = D > 1u ? 0xffffffffu / D + 1u : 0u;
+      }
+      fl = (int)c;
+      const unsigned tot = c * D;  // c <= kPadCap, D < 2^31 / kPadCap whenever it matters
+      R = (D > (unsigned)kPadCap || tot > (unsigned)kPadCap) ? (unsigned)kRounds + 1u
+                                                             : (tot + kNwBlock - 1) / kNwBlock;
+      prev_begin = lvl_begin;
+      lvl_begin += x.ctotal;
+      depth++;
+      nlevels++;
+      written = false;
+      reloaded = false;
       // the shares of the level just expanded: re-split when they have drifted apart (or when
       // one of them nears the capacity an even split would stay well below)
       const unsigned even = (x.ctotal + C - 1u) / C, dd = x.dmax > 0u ? x.dmax : 1u;
       if (C > 1u && (x.cmax > 2u * even + 32u ||
                      ((unsigned long long)x.cmax * dd > (unsigned long long)kPadCap * 3 / 4 &&
                       (unsigned long long)even * dd <= (unsigned long long)kPadCap / 2)))
-        s.need_reload = 1;
-    } else if (lane == 3 && a.max_cluster > 0) {
-      // cluster sizing on the running mean of the padded slots per level
-      const unsigned long long work = (unsigned long long)x.ctotal * (x.dmax > 0u ? x.dmax : 1u);
-      const unsigned long long acc =
-          s.work_acc == ~0ull ? work * 16ull : s.work_acc - s.work_acc / 16ull + work;
-      s.work_acc = acc;
-      const int since = ++s.since_resize;
-      if (since >= 32) {
-        const unsigned long long mean = acc / 16ull;
-        const bool grow = (int)C < a.max_cluster && mean > (unsigned long long)a.grow_above * C;
-        const bool shrink = C > 1u && mean < (unsigned long long)a.shrink_below * C;
-        if (grow || shrink) {
-          int want = 1;
-          while (want < a.max_cluster && (unsigned long long)want * a.target < mean) want <<= 1;
-          if (want != (int)C) s.want_resize = want;
+        need_reload = 1;
+      if (a.max_cluster > 0) {  // cluster sizing on the running mean of the padded slots
+        const unsigned long long work = (unsigned long long)x.ctotal * dd;
+        acc = acc == ~0ull ? work * 16ull : acc - acc / 16ull + work;
+        if (++since >= 32) {
+          const unsigned long long mean = acc / 16ull;
+          const bool grow = (int)C < a.max_cluster && mean > (unsigned long long)a.grow_above * C;
+          const bool shrink = C > 1u && mean < (unsigned long long)a.shrink_below * C;
+          if (grow || shrink) {
+            int want = 1;
+            while (want < a.max_cluster && (unsigned long long)want * a.target < mean) want <<= 1;
+            if (want != (int)C) want_resize = want;
+          }
         }
       }
     }
+    if (need_reload || want_resize) {
+      ret = 1;
+      break;
+    }
+    __syncthreads();  // the next share is complete
+    SB_TICK(4);
   }
-  if (CM) {
-    __syncthreads();
-    // (parent, degree, id) order: the winners of one parent are adjacent in slot order and never
-    // leave the CTA that owns the parent; rank inside the sibling group by enumeration
-    for (int k = threadIdx.x; k < (int)c; k += kNwBlock) {
-      const unsigned par_i = s.Sp[k], dgk = s.Sd[k];
-      const I vk = s.Sv[k];
-      const int64_t xk = s.Sx[k];
-      const bool has_l = k > 0 && s.Sp[k - 1] == par_i;
-      const bool has_r = k + 1 < (int)c && s.Sp[k + 1] == par_i;
-      int dst = k;
-      if (has_l || has_r) {  // (an only child stays where it is)
-        int left = 0, before = 0;
-        for (int q0 = k - 1; has_l && q0 >= 0; q0 -= 4) {
-          int nm = 0;
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int q = q0 - u;
-            if (q >= 0 && s.Sp[q] == par_i) {
-              nm++;
-              before += (s.Sd[q] < dgk || (s.Sd[q] == dgk && s.Sv[q] < vk)) ? 1 : 0;
-            }
-          }
-          left += nm;
-          if (nm < 4) break;
-        }
-        for (int q0 = k + 1; has_r && q0 < (int)c; q0 += 4) {
-          int nm = 0;
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int q = q0 + u;
-            if (q < (int)c && s.Sp[q] == par_i) {
-              nm++;
-              before += (s.Sd[q] < dgk || (s.Sd[q] == dgk && s.Sv[q] < vk)) ? 1 : 0;
-            }
-          }
-          if (nm < 4) break;
-        }
-        dst = k - left + before;
-      }
-      s.Fv[dst] = vk;
-      s.Fx[dst] = xk;
-      s.Fd[dst] = dgk;
-    }
+#undef SB_TICK
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s.fl = fl;
+    s.D = D;
+    s.invD = invD;
+    s.rounds = R;
+    s.S.lvl_begin = lvl_begin;
+    s.S.prev_begin = prev_begin;
+    s.S.lvl_end = lvl_end;
+    s.S.depth = depth;
+    s.S.frontier_maxdeg = frontier_maxdeg;
+    s.S.stat_levels_narrow += nlevels;
+    s.share_written = written ? 1 : 0;
+    s.just_reloaded = reloaded ? 1 : 0;
+    if (need_reload) s.need_reload = 1;
+    if (want_resize) s.want_resize = want_resize;
+    s.work_acc = acc;
+    s.since_resize = since;
   }
   __syncthreads();
-  SB_TICK(4);
-#undef SB_TICK
-  return 1;
+  return ret;
 }
 
 // min over queue[b, e) of (degree << 32 | position - b); *ties = how many vertices of the slice
@@ -833,9 +879,9 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
         break;
       }
       if (s.need_reload) cl_reload<I, N>(cluster, a, s, queue, lxstate);
-      const int r = phase == PH_PBFS_LEVEL ? cl_level<I, N, false>(cluster, a, s, queue, lxstate)
-                                           : cl_level<I, N, true>(cluster, a, s, queue, lxstate);
-      if (r == 1) continue;
+      const int r = phase == PH_PBFS_LEVEL ? cl_levels<I, N, false>(cluster, a, s, queue, lxstate)
+                                           : cl_levels<I, N, true>(cluster, a, s, queue, lxstate);
+      if (r == 1) continue;  // (re-split or resize pending)
       if (r == 0) {
         if (threadIdx.x == 0) s.S.phase = phase == PH_PBFS_LEVEL ? PH_PBFS_END : PH_CM_END;
         __syncthreads();

@@ -27,7 +27,7 @@ SYMBOLS = [
     "sb200_rcm_last_resplits",
     "sb200_rcm_last_speculation", "sb200_permute2d", "sb200_permute1d",
     "sb200_inverse_permutation",
-    "sb200_degrees", "sb200_degree_distribution", "sb200_partition_rows", "sb200_launch_count",
+    "sb200_degrees", "sb200_degree_distribution", "sb200_degree_features", "sb200_edges_to_coo", "sb200_partition_rows", "sb200_launch_count",
     "sb200_reset_launch_count", "sb200_coo_to_csr_block", "sb200_csr_to_csc_block",
     "sb200_exclusive_scan", "sb200_rank_keys", "sb200_max_degree", "sb200_degree_histogram",
     "sb200_degree_rank_combine",
@@ -253,6 +253,42 @@ def degree_distribution(n, nnz, row_ptr, feature_dtype=torch.float32):
                                             _p(out), _DT[row_ptr.dtype], _DT[feature_dtype],
                                             _stream(row_ptr)))
     return out
+
+
+def degree_features(n, nnz, row_ptr, col=None, id_dtype=torch.int32,
+                    feature_dtype=torch.float32, want_arrays=True):
+    """Fused Degrees_DegreeDistribution + min/max/avg degree + Bandwidth + Profile.
+    Returns (degrees, dist, dict(min_degree, max_degree, bandwidth, profile, avg_degree))."""
+    deg = torch.empty(n, dtype=id_dtype, device=row_ptr.device) if want_arrays else None
+    dist = torch.empty(n, dtype=feature_dtype, device=row_ptr.device) if want_arrays else None
+    sc = (ctypes.c_int64 * 4)()
+    avg = ctypes.c_double(0.0)
+    _check(load().sb200_degree_features(_dev(row_ptr), _i64(n), _i64(nnz), _p(row_ptr), _p(col),
+                                        _p(deg), _p(dist), sc, ctypes.byref(avg),
+                                        _DT[id_dtype], _DT[row_ptr.dtype], _DT[feature_dtype],
+                                        _stream(row_ptr)))
+    out = dict(zip(("min_degree", "max_degree", "bandwidth", "profile"), (int(x) for x in sc)))
+    out["avg_degree"] = avg.value
+    return deg, dist, out
+
+
+def edges_to_coo(u, v, w=None, remove_duplicates=True, remove_self_edges=False,
+                 read_undirected=False, square=False):
+    """EdgeListReader::ReadCOO on a device edge list: returns (n, m, row, col, vals), sorted by
+    (row, col) and de-duplicated."""
+    cap = max(1, u.numel() * (2 if read_undirected else 1))
+    orow = torch.empty(cap, dtype=u.dtype, device=u.device)
+    ocol = torch.empty(cap, dtype=u.dtype, device=u.device)
+    oval = None if w is None else torch.empty(cap, dtype=w.dtype, device=u.device)
+    out3 = (ctypes.c_int64 * 3)()
+    _check(load().sb200_edges_to_coo(_dev(u), _i64(u.numel()), _p(u), _p(v), _p(w),
+                                     ctypes.c_int(int(remove_duplicates)),
+                                     ctypes.c_int(int(remove_self_edges)),
+                                     ctypes.c_int(int(read_undirected)), ctypes.c_int(int(square)),
+                                     _p(orow), _p(ocol), _p(oval), out3, _DT[u.dtype], _vt(w),
+                                     _stream(u)))
+    n, m, nnz = (int(x) for x in out3)
+    return n, m, orow[:nnz], ocol[:nnz], None if oval is None else oval[:nnz]
 
 
 def partition_rows(n, nnz, row_ptr, parts):

@@ -28,7 +28,16 @@ def hash_vals(count, seed=1, device="cpu", dtype=torch.float32):
 
 
 def _finish(n, r, c, symmetrise=True, drop_self=True, id_dtype=torch.int32):
-    """symmetrise + dedupe + sort by (row, col) through unique() on row*n + col."""
+    """symmetrise + dedupe + sort by (row, col).  On a CUDA device this is the library's own
+    edge-list -> COO path (sb200_edges_to_coo: EdgeListReader semantics, radix sort + unique in
+    libsb200.so, no library sort); on the CPU (test plumbing without a GPU) unique() on
+    row*n + col gives the same arrays."""
+    if r.is_cuda:
+        from . import lib
+        _, _, row, col, _ = lib.edges_to_coo(r.to(id_dtype), c.to(id_dtype), None,
+                                             remove_duplicates=True, remove_self_edges=drop_self,
+                                             read_undirected=symmetrise, square=True)
+        return n, row.clone(), col.clone()
     if drop_self:
         keep = r != c
         r, c = r[keep], c[keep]

@@ -199,6 +199,38 @@ class Oracle:
         assert rc == 0
         return out
 
+    def degree_features(self, n, row_ptr, col, vals_dtype=np.float32):
+        """(degrees, dist, {min_degree, max_degree, bandwidth, profile}, avg_degree)."""
+        row_ptr, col = _c(row_ptr), _c(col)
+        t = tag_of(col.dtype, row_ptr.dtype, vals_dtype)
+        deg = np.empty(n, col.dtype)
+        dist = np.empty(n, _FEAT[t])
+        sc = (ctypes.c_int64 * 4)()
+        avg = np.zeros(1, _FEAT[t])
+        rc = self._fn(f"degree_features_{t}")(self._i64(n), self._i64(n), _ptr(row_ptr), _ptr(col),
+                                              _ptr(deg), _ptr(dist), sc, _ptr(avg))
+        assert rc == 0
+        return deg, dist, dict(zip(("min_degree", "max_degree", "bandwidth", "profile"),
+                                   (int(x) for x in sc))), avg[0]
+
+    def edges_to_coo(self, u, v, w=None, remove_duplicates=True, remove_self=False,
+                     undirected=False, square=False, nnz_dtype=np.int32):
+        """EdgeListReader::ReadCOO semantics on arrays: returns (n, m, row, col, vals)."""
+        u, v, w = _c(u), _c(v), _c(w)
+        t = tag_of(u.dtype, nnz_dtype, None if w is None else w.dtype)
+        cap = max(1, len(u) * (2 if undirected else 1))
+        orow, ocol = np.empty(cap, u.dtype), np.empty(cap, u.dtype)
+        ov = None if w is None else np.empty(cap, w.dtype)
+        out3 = (ctypes.c_int64 * 3)()
+        rc = self._fn(f"edges_to_coo_{t}")(self._i64(len(u)), _ptr(u), _ptr(v), _ptr(w),
+                                           ctypes.c_int(int(remove_duplicates)),
+                                           ctypes.c_int(int(remove_self)),
+                                           ctypes.c_int(int(undirected)), ctypes.c_int(int(square)),
+                                           _ptr(orow), _ptr(ocol), _ptr(ov), out3)
+        assert rc == 0
+        n, m, nnz = (int(x) for x in out3)
+        return n, m, orow[:nnz].copy(), ocol[:nnz].copy(), None if ov is None else ov[:nnz].copy()
+
 
 def build_oracle():
     """Compile oracle/liboracle.so (and _ref/libsbref.so when /root/reference is mounted)."""

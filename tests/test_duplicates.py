@@ -24,8 +24,10 @@ LENGTHS = [5, 40, 200, 3000]
 def dup_matrix(maxlen, idt, nt, vt, seed, sorted_rows):
     """n x n CSR with many repeated column ids per row and DISTINCT mixed-sign values."""
     rng = np.random.default_rng(seed)
-    n = 2003 if maxlen <= 200 else 307
-    deg = rng.integers(0, maxlen + 1, size=n)
+    n = 2003 if maxlen <= 200 else 4001
+    deg = rng.integers(0, maxlen + 1, size=n) if maxlen <= 200 else rng.integers(0, 60, size=n)
+    if maxlen > 200:
+        deg[rng.integers(0, n, size=40)] = rng.integers(1025, maxlen + 1, size=40)
     deg[[1, n // 2]] = maxlen
     deg[rng.integers(0, n, size=n // 20)] = 0
     cols = []
