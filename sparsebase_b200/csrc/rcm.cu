@@ -865,6 +865,12 @@ __global__ void __launch_bounds__(kNwBlock, 1) rcm_narrow_kernel(RcmArgs<I, N> a
     if (phase == PH_PBFS_LEVEL || phase == PH_CM_LEVEL) {
       I *queue = phase == PH_PBFS_LEVEL ? a.Qp : a.Q;
       if (a.force_wide) {  // (the frontier is always in the queue here)
+        if (s.S.lvl_end == s.S.lvl_begin) {  // the wide regime emptied it: the BFS is complete
+          __syncthreads();
+          if (threadIdx.x == 0) s.S.phase = phase == PH_PBFS_LEVEL ? PH_PBFS_END : PH_CM_END;
+          __syncthreads();
+          continue;
+        }
         if (threadIdx.x == 0) s.S.status = ST_NEED_WIDE;
         break;
       }
