@@ -1,20 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the hot path (contract: see the task statement / DESIGN.md).
+"""bench.py -- headline benchmark of the hot path (contract: the task statement / DESIGN.md 5).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--grid G]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scale S]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], "C2"): RCMReorder + Permute2D on a synthetic 2-D Poisson
-5-point stencil, G x G grid (default 4096 -> 16.7 M rows, 83.9 M nnz), IDType=NNZType=int32,
-ValueType=float32.  A "step" is one pass of the path over that matrix:
-    inv = RCMReorder(csr);  out = Permute2D(inv, csr)
-`value` is nonzeros per second (GNNZ/s) of the whole step with the CSR resident in HBM;
-`e2e` is the same step through the C ABI with HOST (pinned) buffers: H2D of the CSR, the two
-operators, D2H of the permuted CSR and of the permutation, all inside the timed region.
-With N > 1 ranks (torchrun) every rank runs an independent replica of the workload (RCM does
-not shard: its levels serialise -- "replicas only"), value = N * nnz / max-time.
+Workload (BASELINE.json configs[3], "C4"): COO->CSR + DegreeReorder + Permute2D on a power-law
+R-MAT scale-26 graph (67.1 M vertices, ~1.07 B nnz, IDType = NNZType = int32, ValueType =
+float32), row-block sharded over the N GPUs.  A "step" is one pass of that path over the matrix:
 
---impl reference times the reference's own CPU implementation (oracle/_ref/libsbref.so = the
-unmodified reference compiled header-only; the oracle port if that is absent) on the host.
+    csr = COO->CSR(coo);  inv = DegreeReorder(csr);  out = Permute2D(inv, csr)
+
+At N = 1 these are the single-GPU operators; at N > 1 the peer-memory operators (sb200_mg_*:
+every rank owns an nnz-balanced row block and stores its part of every exchange straight into
+the destination GPU's window over NVLink).  The matrix is the same at every N (strong scaling);
+`value` = nnz / (step time, max over ranks) with the shards resident in HBM; `e2e` is the same
+step with HOST (pinned) shards in and out.  Beside the headline the line carries
+  ops      per-operator ms / GNNZ/s / fraction of the HBM roofline (x N GPUs)
+  c3       configs[2]: CSR->CSC + DegreeDistribution on Erdos-Renyi 2^24 x 16 (268 M nnz)
+  rcm      configs[1] (N = 1): RCMReorder + Permute2D on 2-D Poisson 4096^2 in ms, checked
+           byte for byte against the compiled reference; bandwidth before / after
+  parity   the headline result checked against the oracle (sampled rows + checksums)
+
+--impl reference times the reference's own CPU implementation of the same path
+(oracle/_ref/libsbref.so = the unmodified reference compiled header-only; the C restatement if
+that is absent) on a bounded R-MAT sample of the workload, with all host threads.
 """
 import argparse
 import json
@@ -27,13 +36,28 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+def _set_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the reference's OpenMP regions (the constructor row
+    sort) get every host core, and the line says how many."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
+
+
+HOST_THREADS = _set_host_threads()
+
 import torch  # noqa: E402
 
-ALG_BYTES_PERMUTE2D = lambda n, nnz: nnz * 16 + 2 * (n + 1) * 4 + 2 * n * 4  # noqa: E731
+WORKLOAD = ("C4: COO->CSR + DegreeReorder + Permute2D on R-MAT scale {scale} (edge factor 8 "
+            "undirected, a,b,c = 0.57,0.19,0.19, seed 44), IDType=NNZType=int32, ValueType=float32, "
+            "nnz-balanced row blocks over the GPUs")
+METRIC = "coo_csr_degreereorder_permute2d_gnnz_per_s"
+
 ALG_BYTES = {  # SURVEY.md section 8(d), I = N = V = 4 bytes
     "coo_to_csr": lambda n, nnz: nnz * 20 + (n + 1) * 4,
     "csr_to_csc": lambda n, nnz: nnz * 16 + 2 * (n + 1) * 4,
-    "permute2d": ALG_BYTES_PERMUTE2D,
+    "permute2d": lambda n, nnz: nnz * 16 + 2 * (n + 1) * 4 + 2 * n * 4,
     "degree_reorder": lambda n, nnz: (n + 1) * 4 + n * 4,
     "degree_distribution": lambda n, nnz: (n + 1) * 4 + n * 4,
 }
@@ -48,13 +72,13 @@ def peaks():
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the Permute2D kernels of this workload,
-    per launch, from the committed `ncu --set full` capture (profiles/*_traffic.json)."""
-    path = os.path.join(ROOT, "profiles", "r1_e_traffic.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the
+    committed `ncu --set full` capture (profiles/r2_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
-        return json.load(f).get("permute2d_dram_bytes_per_launch")
+        return json.load(f).get("permute2d_gather_dram_bytes_per_launch")
 
 
 class ClockSampler:
@@ -110,69 +134,183 @@ def dist_env():
             int(os.environ.get("WORLD_SIZE", 1)))
 
 
-# ------------------------------------------------------------------------ reference arm
-def cpu_reference_step(grid, reps=1):
-    """Times the reference's CPU path (RCMReorder + Permute2D) on a grid x grid Poisson matrix.
-    Returns dict(value GNNZ/s, seconds, kind, cores, sample)."""
+# ------------------------------------------------------------------------ CPU arms
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import numpy as np
     import oracle_lib
-    from sparsebase_b200 import synth
-
     ref = oracle_lib.reference()
-    kind = "reference"
-    if ref is None:
-        ref, kind = oracle_lib.restated(), "port"
-    n, rp, col, vals = synth.poisson2d(grid, grid)
-    rp, col, vals = rp.numpy(), col.numpy(), vals.numpy()
+    if ref is not None:
+        return ref, "reference", oracle_lib
+    return oracle_lib.restated(), "port", oracle_lib
+
+
+def cpu_pipeline_step(scale, graph=None):
+    """The reference's CPU path for the headline workload on an R-MAT sample of `scale`:
+    COO->CSR (converter_order_two.cc:162-212), DegreeReorder (degree_reorder.cc:22-62),
+    Permute2D (permute_order_two.cc:21-79 + the CSR constructor sort)."""
+    from sparsebase_b200 import synth
+    ref, kind, _ = _oracle()
+    if graph is None:
+        n, row, col = synth.rmat(scale, 8, seed=44)
+        vals = synth.hash_vals(col.numel(), seed=7)
+        graph = (n, row.numpy(), col.numpy(), vals.numpy())
+    n, row, col, vals = graph
     nnz = len(col)
-    best, parts = None, None
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        inv = ref.rcm_reorder(n, rp, col, vals)
-        t1 = time.perf_counter()
-        out = ref.permute2d(n, n, rp, col, vals, inv, inv)
-        t2 = time.perf_counter()
-        if best is None or t2 - t0 < best:
-            best, parts = t2 - t0, (t1 - t0, t2 - t1)
-        del out
-    cores = os.cpu_count() if kind == "reference" else 1
-    return {"value": nnz / best / 1e9, "unit": "GNNZ/s", "seconds": best, "rcm_s": parts[0],
-            "permute2d_s": parts[1], "kind": kind, "cores": cores, "nnz": nnz, "n": n,
-            "sample": f"RCMReorder+Permute2D on Poisson {grid}x{grid} ({n} rows, {nnz} nnz), "
-                      f"best of {reps}; OpenMP threads = {cores} (only the CSR-ctor row sort is "
-                      "parallel in the reference)"}
+    t0 = time.perf_counter()
+    rp, cc, vv = ref.coo_to_csr(n, n, row, col, vals)
+    t1 = time.perf_counter()
+    inv = ref.degree_reorder(n, rp, cc, True, vv)
+    t2 = time.perf_counter()
+    out = ref.permute2d(n, n, rp, cc, vv, inv, inv)
+    t3 = time.perf_counter()
+    del out
+    cores = HOST_THREADS if kind == "reference" else 1
+    return {"value": nnz / (t3 - t0) / 1e9, "unit": "GNNZ/s", "seconds": t3 - t0,
+            "coo_to_csr_s": t1 - t0, "degree_reorder_s": t2 - t1, "permute2d_s": t3 - t2,
+            "kind": kind, "cores": cores, "nnz": nnz, "n": n,
+            "sample": f"the same path on R-MAT scale {scale} ({n} rows, {nnz} nnz; same generator "
+                      f"and seed as the workload); OpenMP threads = {cores} (set explicitly; only "
+                      "the CSR-constructor row check / sort is parallel in the reference); the "
+                      "harness replaces operator new[] by calloc + 64 B (reference heap overflow "
+                      "in degree_reorder.cc:41-45), which is also the timed allocator"}, graph
 
 
 def run_reference(args):
-    rank, _, world = dist_env()
+    rank, _, _ = dist_env()
     if rank != 0:
         return
     total = args.steps + args.warmup
-    grid = min(args.grid, 2048 if total <= 12 else 1024)
+    scale = args.ref_scale if total <= 10 else max(16, args.ref_scale - 1)
     for _ in range(args.warmup):
-        cpu_reference_step(min(grid, 512))
-    t = []
-    r = None
+        cpu_pipeline_step(min(scale, 16))
+    graph, t, r = None, [], None
     for _ in range(args.steps):
-        r = cpu_reference_step(grid)
+        r, graph = cpu_pipeline_step(scale, graph)
         t.append(r["seconds"])
     sec = sum(t) / len(t)
     value = r["nnz"] / sec / 1e9
     line = {
-        "impl": "reference", "metric": "rcm_permute2d_gnnz_per_s", "value": value,
-        "unit": "GNNZ/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GNNZ/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"C2: RCMReorder+Permute2D, 2-D Poisson 5-point {args.grid}x"
-                               f"{args.grid}; reference arm runs the bounded sample below"},
-        "cpu_baseline": {"value": value, "unit": "GNNZ/s", "cores": r["cores"],
-                         "kind": r["kind"], "sample": r["sample"]},
+        "config": {"workload": WORKLOAD.format(scale=args.scale)},
+        "cpu_baseline": {"value": value, "unit": "GNNZ/s", "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["sample"], "coo_to_csr_s": r["coo_to_csr_s"],
+                         "degree_reorder_s": r["degree_reorder_s"], "permute2d_s": r["permute2d_s"]},
         "e2e": {"value": value, "unit": "GNNZ/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------ parity helpers
+def check_headline(lib, n, g_rp, g_col, g_val, inv, out_rows, out_shard, nsamp=500):
+    """The headline result against the oracle: DegreeReorder's order and tie rule over the whole
+    permutation, Permute2D's row_ptr / checksums over the rank's whole block, and `nsamp` rows of
+    the block against the C restatement run on a matrix made of exactly those rows.
+    out_rows = (nlo, nhi); out_shard = (row_ptr block-local, col, vals)."""
+    import ctypes
+    import numpy as np
+    _, _, oracle_lib = _oracle()
+    orc = oracle_lib.restated()
+    dev = g_rp.device
+    res = {}
+    deg = (g_rp[1:] - g_rp[:-1]).to(torch.int64)
+    order = torch.empty(n, dtype=torch.int64, device=dev)
+    order[inv.to(torch.int64)] = torch.arange(n, device=dev)
+    res["inv_is_permutation"] = bool((torch.bincount(inv.to(torch.int64), minlength=n) == 1).all())
+    d_sorted = deg[order]
+    tie = d_sorted[1:] == d_sorted[:-1]
+    res["degree_order_and_tie_rule"] = bool((d_sorted[1:] >= d_sorted[:-1]).all()) and \
+        bool((order[1:][tie] < order[:-1][tie]).all())
+    nlo, nhi = out_rows
+    orp, ocol, oval = out_shard
+    res["row_ptr"] = bool(((orp[1:] - orp[:-1]).to(torch.int64) == d_sorted[nlo:nhi]).all())
+    del d_sorted, tie
+    # sampled rows of my block
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    new_rows = (torch.randint(0, max(1, nhi - nlo), (nsamp,), generator=g, device=dev) + nlo).unique()
+    old_rows = order[new_rows]
+    h_old, h_new = old_rows.cpu().numpy(), new_rows.cpu().numpy()
+    h_rp = g_rp.cpu().numpy()
+    h_orp = orp.cpu().numpy()
+    h_inv = inv.cpu().numpy()
+    sub_rp = np.zeros(len(h_old) + 1, dtype=h_rp.dtype)
+    pc, pv = [], []
+    for k, r in enumerate(h_old):
+        a, b = int(h_rp[r]), int(h_rp[r + 1])
+        pc.append(g_col[a:b].cpu().numpy())
+        pv.append(g_val[a:b].cpu().numpy())
+        sub_rp[k + 1] = sub_rp[k] + (b - a)
+    sub_col, sub_val = np.concatenate(pc), np.concatenate(pv)
+    ident = np.arange(len(h_old), dtype=h_inv.dtype)
+    t = oracle_lib.tag_of(sub_col.dtype, sub_rp.dtype, sub_val.dtype)
+    e_rp = np.empty(len(h_old) + 1, sub_rp.dtype)
+    e_col, e_val = np.empty_like(sub_col), np.empty_like(sub_val)
+    P = oracle_lib._ptr
+    rc = orc._fn(f"permute2d_{t}")(ctypes.c_int64(len(h_old)), ctypes.c_int64(n), P(sub_rp),
+                                   P(sub_col), P(sub_val), P(ident), P(h_inv), P(e_rp), P(e_col),
+                                   P(e_val))
+    ok = rc == 0
+    for k, j in enumerate(h_new):
+        a, b = int(h_orp[j - nlo]), int(h_orp[j - nlo + 1])
+        ea, eb = int(e_rp[k]), int(e_rp[k + 1])
+        ok = ok and (b - a == eb - ea) and np.array_equal(ocol[a:b].cpu().numpy(), e_col[ea:eb]) \
+            and np.array_equal(oval[a:b].cpu().numpy().view(np.uint32), e_val[ea:eb].view(np.uint32))
+    res["sampled_rows_vs_oracle"] = bool(ok)
+    res["rows_sampled"] = int(len(h_new))
+    return res
+
+
+def rcm_block(lib, dev, peak, grid=4096, reps=3):
+    """configs[1]: RCMReorder + Permute2D on the 2-D Poisson grid, with the permutation and the
+    permuted matrix compared byte for byte with the reference's CPU result."""
+    import numpy as np
+    from sparsebase_b200 import synth
+    n, rp, col, vals = synth.poisson2d(grid, grid, device=dev)
+    nnz = col.numel()
+    out = (torch.empty_like(rp), torch.empty_like(col), torch.empty_like(vals))
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(reps)]
+    inv = lib.rcm_reorder(n, rp, col)
+    lib.permute2d(n, n, rp, col, vals, inv, inv, out=out)
+    torch.cuda.synchronize()
+    for k in range(reps):
+        ev[k][0].record()
+        inv = lib.rcm_reorder(n, rp, col)
+        ev[k][1].record()
+        lib.permute2d(n, n, rp, col, vals, inv, inv, out=out)
+        ev[k][2].record()
+    torch.cuda.synchronize()
+    rcm_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / reps
+    p2d_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / reps
+    st = lib.rcm_last_stats()
+    _, _, before = lib.degree_features(n, nnz, rp, col, want_arrays=False)
+    _, _, after = lib.degree_features(n, nnz, out[0], out[1], want_arrays=False)
+    ref, kind, _ = _oracle()
+    h = [t.cpu().numpy() for t in (rp, col, vals)]
+    t0 = time.perf_counter()
+    e_inv = ref.rcm_reorder(n, h[0], h[1], h[2])
+    t1 = time.perf_counter()
+    e_out = ref.permute2d(n, n, h[0], h[1], h[2], e_inv, e_inv)
+    t2 = time.perf_counter()
+    same = np.array_equal(inv.cpu().numpy(), e_inv) and all(
+        np.array_equal(a.cpu().numpy().view(np.uint8), b.view(np.uint8)) for a, b in zip(out, e_out))
+    p2d_gbs = ALG_BYTES["permute2d"](n, nnz) / (p2d_ms * 1e-3) / 1e9
+    return {"workload": f"C2: RCMReorder + Permute2D on 2-D Poisson 5-point {grid}x{grid} "
+                        f"({n} rows, {nnz} nnz)",
+            "rcm_ms": rcm_ms, "permute2d_ms": p2d_ms, "gnnz_per_s": nnz / ((rcm_ms + p2d_ms) * 1e-3) / 1e9,
+            "permute2d_roofline_frac": p2d_gbs / peak,
+            "levels": st["levels_narrow"] + st["levels_wide"], "levels_wide": st["levels_wide"],
+            "us_per_level": rcm_ms * 1e3 / max(1, st["levels_narrow"] + st["levels_wide"]),
+            "bfs": st["bfs"], "cluster_resizes": st["resizes"], "share_resplits": st["resplits"],
+            "bandwidth_before": before["bandwidth"], "bandwidth_after": after["bandwidth"],
+            "profile_before": before["profile"], "profile_after": after["profile"],
+            "parity_vs_reference": bool(same), "parity_checker": kind,
+            "cpu": {"rcm_s": t1 - t0, "permute2d_s": t2 - t1, "kind": kind, "cores": HOST_THREADS,
+                    "gnnz_per_s": nnz / (t2 - t0) / 1e9}}
 
 
 # ------------------------------------------------------------------------ our arm
@@ -182,9 +320,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sb200")
-    ap.add_argument("--grid", type=int, default=4096)
+    ap.add_argument("--scale", type=int, default=26)
+    ap.add_argument("--ref-scale", type=int, default=21)
+    ap.add_argument("--cpu-scale", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-grid", type=int, default=2048)
+    ap.add_argument("--no-rcm", action="store_true")
+    ap.add_argument("--no-c3", action="store_true")
+    ap.add_argument("--c3-log2n", type=int, default=24)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -196,219 +338,253 @@ def main():
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from sparsebase_b200 import lib, synth
+    from sparsebase_b200 import lib, mg, sharded, synth
     lib.load()
     dev = torch.device("cuda", local_rank)
     W = max(args.warmup, 3)
-
-    n, row_ptr, col, vals = synth.poisson2d(args.grid, args.grid, device=dev)
-    nnz = col.numel()
-    out = (torch.empty_like(row_ptr), torch.empty_like(col), torch.empty_like(vals))
-
-    def step():
-        inv = lib.rcm_reorder(n, row_ptr, col)
-        lib.permute2d(n, n, row_ptr, col, vals, inv, inv, out=out)
-        return inv
+    peak, peak_src = peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    # ---- the matrix (identical on every rank: same generator, same seed, same hardware)
+    n, row, col = synth.rmat(args.scale, 8, seed=44, device=dev)
+    nnz = col.numel()
+    vals = synth.hash_vals(nnz, seed=7, device=dev)
+    torch.cuda.empty_cache()
+    g_rp, g_col, g_val = lib.coo_to_csr(n, n, row, col, vals)   # set-up: blocks + parity checks
+    bounds = lib.partition_rows(n, nnz, g_rp, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    a, b = int(g_rp[lo]), int(g_rp[hi])
+    if world > 1:
+        r_l, c_l, v_l = row[a:b].clone(), col[a:b].clone(), vals[a:b].clone()
+        del row, col, vals
+        torch.cuda.empty_cache()
+        shard_bytes = (nnz // world + n // world + 4096) * 8
+        window = int(shard_bytes * 1.15) + (n + 1) * 4 + (256 << 20)
+        comm = mg.Comm(window)
+    else:
+        r_l, c_l, v_l = row, col, vals
+        comm = None
+
+    ev = None
+
+    def step(record=None):
+        """-> (inv, (nlo, nhi), (row_ptr', col', vals') of this rank's block)"""
+        if record:
+            record[0].record()
+        if world == 1:
+            csr = lib.coo_to_csr(n, n, r_l, c_l, v_l)
+            if record:
+                record[1].record()
+            inv = lib.degree_reorder(n, csr[0], True)
+            if record:
+                record[2].record()
+            out = lib.permute2d(n, n, csr[0], csr[1], csr[2], inv, inv)
+            if record:
+                record[3].record()
+            return inv, (0, n), out
+        s = mg.coo_to_csr(comm, n, n, bounds, r_l, c_l, v_l, presorted=True)
+        if record:
+            record[1].record()
+        inv = mg.degree_reorder(comm, s, True)
+        if record:
+            record[2].record()
+        p = mg.permute2d(comm, s, inv, inv)
+        if record:
+            record[3].record()
+        return inv, (p.bounds[rank], p.bounds[rank + 1]), (p.row_ptr, p.col, p.vals)
+
     for _ in range(W):
         step()
-    # ---- device-resident timing: K steps, CUDA events, per-operator split ----
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    # ---- device-resident timing: K steps, CUDA events on the launching stream
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     lib.reset_launch_count()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
-        ev[k][0].record()
-        inv = lib.rcm_reorder(n, row_ptr, col)
-        ev[k][1].record()
-        lib.permute2d(n, n, row_ptr, col, vals, inv, inv, out=out)
-        ev[k][2].record()
+        inv, out_rows, out = step(ev[k])
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = lib.launch_count()
     clocks = sampler.stop()
-    total_ms = ev[0][0].elapsed_time(ev[-1][2])
-    rcm_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    p2d_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
-    rcm_stats = lib.rcm_last_stats()
-    ms_per_step = total_ms / args.steps
+    ms_per_step = max_over_ranks(ev[0][0].elapsed_time(ev[-1][3]) / args.steps)
+    op_ms = {name: max_over_ranks(sum(e[i].elapsed_time(e[i + 1]) for e in ev) / args.steps)
+             for i, name in enumerate(("coo_to_csr", "degree_reorder", "permute2d"))}
+    value = nnz / (ms_per_step * 1e-3) / 1e9
+
+    # ---- parity of the headline result (outside the timed region)
+    parity = check_headline(lib, n, g_rp, g_col, g_val, inv, out_rows, out)
+    parity_ok = all(v for k, v in parity.items() if isinstance(v, bool))
     if world > 1:
-        t = torch.tensor([ms_per_step], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_per_step = float(t.item())
-    value = world * nnz / (ms_per_step * 1e-3) / 1e9
+        t = torch.tensor([1.0 if parity_ok else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        parity_ok = bool(t.item() > 0.5)
+    out_sizes = [(t.numel(), t.dtype) for t in out]   # (the same every step)
+    del out
 
-    # ---- end to end: host (pinned) buffers in, host buffers out ----
-    h_in = [t.cpu().pin_memory() for t in (row_ptr, col, vals)]
-    h_out = [torch.empty_like(t).pin_memory() for t in h_in]
-    h_inv = torch.empty(n, dtype=torch.int32).pin_memory()
-    d_in = [torch.empty_like(t) for t in (row_ptr, col, vals)]
+    # ---- end to end: host (pinned) shards in, host shards out
+    h_in = [t.cpu().pin_memory() for t in (r_l, c_l, v_l)]
+    d_in = [torch.empty_like(t) for t in (r_l, c_l, v_l)]
     h2d = sum(t.numel() * t.element_size() for t in h_in)
-    d2h = sum(t.numel() * t.element_size() for t in h_out) + h_inv.numel() * 4
-
-    side = torch.cuda.Stream(device=dev)
+    h_inv = torch.empty(n, dtype=torch.int32).pin_memory() if rank == 0 else None
+    h_out = [torch.empty(cnt, dtype=dt).pin_memory() for cnt, dt in out_sizes]
+    d2h_box = [0]
 
     def e2e_step():
-        # RCM needs the pattern only: the values travel on a second stream while it runs, and
-        # the permutation goes back to the host while Permute2D runs
-        main = torch.cuda.current_stream(dev)
-        d_in[0].copy_(h_in[0], non_blocking=True)
-        d_in[1].copy_(h_in[1], non_blocking=True)
-        side.wait_stream(main)          # previous step's readers of d_in[2] are done
-        with torch.cuda.stream(side):
-            d_in[2].copy_(h_in[2], non_blocking=True)
-        inv = lib.rcm_reorder(n, d_in[0], d_in[1])
-        main.wait_stream(side)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            h_inv.copy_(inv, non_blocking=True)
-        lib.permute2d(n, n, d_in[0], d_in[1], d_in[2], inv, inv, out=out)
-        for h, d in zip(h_out, out):
-            h.copy_(d, non_blocking=True)
-        main.wait_stream(side)
+        nonlocal r_l, c_l, v_l
+        for d, h in zip(d_in, h_in):
+            d.copy_(h, non_blocking=True)
+        keep = (r_l, c_l, v_l)
+        r_l, c_l, v_l = d_in
+        inv2, _, o = step()
+        r_l, c_l, v_l = keep
+        bytes_out = 0
+        for h, d in zip(h_out, o):
+            h[: d.numel()].copy_(d, non_blocking=True)
+            bytes_out += d.numel() * d.element_size()
+        if h_inv is not None:
+            h_inv.copy_(inv2, non_blocking=True)
+            bytes_out += n * 4
+        d2h_box[0] = bytes_out
 
     e2e_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 3))
     e0.record()
     for _ in range(e2e_steps):
         e2e_step()
     e1.record()
     barrier()
-    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
+    e2e_value = nnz / (e2e_ms * 1e-3) / 1e9
+    h2d_total, d2h_total = h2d, d2h_box[0]
     if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world * nnz / (e2e_ms * 1e-3) / 1e9
+        t = torch.tensor([float(h2d), float(d2h_box[0])], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        h2d_total, d2h_total = int(t[0].item()), int(t[1].item())
+    del h_in, h_out, d_in, h_inv
 
-    # ---- other operators of the path on the same matrix (reported, not the headline) ----
-    peak, peak_src = peaks()
-    ops = {"rcm_reorder": {"ms": rcm_ms, "levels_narrow": rcm_stats["levels_narrow"],
-                           "levels_wide": rcm_stats["levels_wide"], "bfs": rcm_stats["bfs"],
-                           "phase_cycles": rcm_stats["phase_cycles"]}}
-
-    def time_op(name, fn, reps=5):
-        fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / reps
+    # ---- per-operator figures of the headline workload
+    ops = {}
+    for name, ms in op_ms.items():
         gbs = ALG_BYTES[name](n, nnz) / (ms * 1e-3) / 1e9
         ops[name] = {"ms": ms, "gnnz_per_s": nnz / (ms * 1e-3) / 1e9, "alg_gb_per_s": gbs,
-                     "roofline_frac": gbs / peak}
+                     "roofline_frac": gbs / (peak * world)}
 
-    if rank == 0:
-        row = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int32),
-                                      (row_ptr[1:] - row_ptr[:-1]).to(torch.int64))
-        inv_fixed = inv
-        time_op("permute2d", lambda: lib.permute2d(n, n, row_ptr, col, vals, inv_fixed, inv_fixed,
-                                                   out=out))
-        time_op("coo_to_csr", lambda: lib.coo_to_csr(n, n, row, col, vals))
-        time_op("csr_to_csc", lambda: lib.csr_to_csc(n, n, row_ptr, col, vals))
-        time_op("degree_reorder", lambda: lib.degree_reorder(n, row_ptr, True))
-        time_op("degree_distribution", lambda: lib.degree_distribution(n, nnz, row_ptr))
-        del row
+    # ---- configs[2] (C3): CSR->CSC + DegreeDistribution on Erdos-Renyi 2^24 x 16
+    c3 = None
+    if not args.no_c3:
+        del g_col, g_val, r_l, c_l, v_l
+        torch.cuda.empty_cache()
+        lib.trim()
+        n3, row3, col3 = synth.erdos_renyi(1 << args.c3_log2n, 8, seed=43, device=dev)
+        nnz3 = col3.numel()
+        val3 = synth.hash_vals(nnz3, seed=7, device=dev)
+        rp3, cc3, cv3 = lib.coo_to_csr(n3, n3, row3, col3, val3)
+        del row3, col3, val3
 
-    # ---- N > 1: the row-block sharded operators on the same matrix (strong scaling: the C2
-    #      matrix split into `world` nnz-balanced row blocks; max time over ranks, exchanges
-    #      included; aggregate roofline = world x per-GPU peak) ----
-    ops_sharded = None
-    if world > 1:
-        from sparsebase_b200 import sharded
-        bounds = lib.partition_rows(n, nnz, row_ptr, world)
-        lo, hi = bounds[rank], bounds[rank + 1]
-        a, b = int(row_ptr[lo]), int(row_ptr[hi])
-        deg_l = (row_ptr[lo + 1:hi + 1] - row_ptr[lo:hi]).to(torch.int64)
-        row_l = torch.repeat_interleave(torch.arange(lo, hi, device=dev, dtype=torch.int32), deg_l)
-        col_l, val_l = col[a:b].contiguous(), vals[a:b].contiguous()
-        ops_sharded = {}
-
-        def time_sharded(name, fn, reps=3):
+        def timed(fn, reps=5):
             fn()
             barrier()
-            e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e_a.record()
+            x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x.record()
             for _ in range(reps):
-                fn()
-            e_b.record()
+                r = fn()
+            y.record()
             barrier()
-            t = torch.tensor([e_a.elapsed_time(e_b) / reps], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            gbs = ALG_BYTES[name](n, nnz) / (ms * 1e-3) / 1e9
-            ops_sharded[name] = {"ms": ms, "gnnz_per_s": nnz / (ms * 1e-3) / 1e9,
-                                 "alg_gb_per_s": gbs, "roofline_frac": gbs / (peak * world)}
+            return max_over_ranks(x.elapsed_time(y) / reps), r
 
-        shard = None
-        try:  # a failure here must not cost the headline line (the error is reported instead)
-            shard = sharded.coo_to_csr(lib, n, n, bounds, row_l.clone(), col_l.clone(),
-                                       val_l.clone())
-            time_sharded("coo_to_csr", lambda: sharded.coo_to_csr(lib, n, n, bounds, row_l, col_l,
-                                                                  val_l, copy=False))
-            time_sharded("csr_to_csc", lambda: sharded.csr_to_csc(lib, shard))
-            time_sharded("permute2d", lambda: sharded.permute2d(lib, shard, inv, inv))
-            time_sharded("degree_reorder", lambda: sharded.degree_reorder(lib, shard, True))
-            time_sharded("degree_distribution", lambda: sharded.degree_distribution(lib, shard))
-        except Exception as exc:  # noqa: BLE001
-            ops_sharded["error"] = f"{type(exc).__name__}: {exc}"[:300]
-        del row_l, col_l, val_l, shard
+        if world == 1:
+            ms_t, csc = timed(lambda: lib.csr_to_csc(n3, n3, rp3, cc3, cv3))
+            ms_d, _ = timed(lambda: lib.degree_distribution(n3, nnz3, rp3))
+            back = lib.csr_to_csc(n3, n3, csc[0], csc[1], csc[2])
+            ok3 = all(torch.equal(x, y) for x, y in zip(back, (rp3, cc3, cv3)))
+        else:
+            s3 = sharded.shard_csr(lib, n3, n3, rp3, cc3, cv3, rank, world)
+            ms_t, cs = timed(lambda: mg.csr_to_csc(comm, s3))
+            ms_d, _ = timed(lambda: sharded.degree_distribution(lib, s3))
+            full = lib.csr_to_csc(n3, n3, rp3, cc3, cv3)     # single-GPU result on every rank
+            clo, chi = cs.bounds[rank], cs.bounds[rank + 1]
+            a3, b3 = int(full[0][clo]), int(full[0][chi])
+            ok3 = torch.equal(cs.col_ptr + a3, full[0][clo:chi + 1]) and \
+                torch.equal(cs.row, full[1][a3:b3]) and torch.equal(cs.vals, full[2][a3:b3])
+            t = torch.tensor([1.0 if ok3 else 0.0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok3 = bool(t.item() > 0.5)
+        c3 = {"workload": f"C3: CSR->CSC + DegreeDistribution on Erdos-Renyi 2^{args.c3_log2n} "
+                          f"vertices, 8 undirected pairs per vertex ({nnz3} nnz)",
+              "parity": bool(ok3),
+              "parity_check": "transpose of the transpose == input" if world == 1 else
+                              "every rank's column block == the slice of the single-GPU result"}
+        for name, ms in (("csr_to_csc", ms_t), ("degree_distribution", ms_d)):
+            gbs = ALG_BYTES[name](n3, nnz3) / (ms * 1e-3) / 1e9
+            c3[name] = {"ms": ms, "gnnz_per_s": nnz3 / (ms * 1e-3) / 1e9, "alg_gb_per_s": gbs,
+                        "roofline_frac": gbs / (peak * world)}
+        del rp3, cc3, cv3
+        torch.cuda.empty_cache()
 
+    if comm is not None:
+        comm.destroy()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    p2d_bytes = ALG_BYTES_PERMUTE2D(n, nnz)
-    achieved = p2d_bytes / (p2d_ms * 1e-3) / 1e9
+    # ---- configs[1] (C2): RCM in ms (one GPU: its levels serialise)
+    rcm = None
+    if world == 1 and not args.no_rcm:
+        lib.trim()
+        rcm = rcm_block(lib, dev, peak)
+
+    p2d = ops["permute2d"]
     line = {
-        "metric": "rcm_permute2d_gnnz_per_s", "value": value, "unit": "GNNZ/s",
-        "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-        "data": "synthetic",
-        "config": {"workload": f"C2: RCMReorder+Permute2D on 2-D Poisson 5-point {args.grid}x"
-                               f"{args.grid} ({n} rows, {nnz} nnz), IDType=NNZType=int32, "
-                               "ValueType=float32",
+        "metric": METRIC, "value": value, "unit": "GNNZ/s", "n_gpus": world, "steps": args.steps,
+        "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(scale=args.scale)},
+        "matrix": {"n": n, "nnz": nnz,
                    "parallelism": "single GPU" if world == 1 else
-                   f"{world} independent replicas (RCM does not shard)",
-                   "l2_policy": "inputs (1.0 GB CSR) larger than the 126 MB L2; no flush needed"},
-        "rcm_ms": rcm_ms, "permute2d_ms": p2d_ms, "wall_ms_per_step": t_wall * 1e3 / args.steps,
+                   f"{world} nnz-balanced row blocks, peer-memory exchanges (sb200_mg_*)",
+                   "l2_policy": "inputs (12.8 GB COO) far larger than the 126 MB L2; no flush needed"},
+        "wall_ms_per_step": t_wall * 1e3 / args.steps,
         "e2e": {"value": e2e_value, "unit": "GNNZ/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "permute_short_rows_kernel (fused gather / "
-                     "renumber / row-sort of Permute2D) + permute_prepare_kernel + "
-                     "scan_lookback_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+        "parity": parity_ok, "parity_detail": parity,
+        "roofline": {"bound": "hbm",
+                     "kernel": "Permute2D gather / renumber / row-sort kernels (ss_tile_kernel + "
+                               "segmented long-row sort) -- the dominant operator of the step",
+                     "achieved": p2d["alg_gb_per_s"] / world, "peak": peak, "unit": "GB/s",
+                     "frac": p2d["roofline_frac"], "traffic": ncu_traffic(),
                      "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": p2d_bytes,
-                     "note": "RCM (rcm_narrow_kernel) is latency-bound level walking and is "
-                             "reported in ms (rcm_ms), not against the HBM roofline"},
+                     "algorithmic_bytes_per_launch": ALG_BYTES["permute2d"](n, nnz) // world,
+                     "note": "achieved is per GPU: algorithmic bytes of Permute2D / N / its time"},
         "ops": ops,
     }
-    if ops_sharded is not None:
-        line["ops_sharded"] = ops_sharded
-        line["ops_sharded_note"] = ("row-block sharded operators on the same C2 matrix split over "
-                                    f"{world} GPUs (strong scaling), exchanges included, max over "
-                                    "ranks; roofline_frac is against world x per-GPU peak")
+    if c3 is not None:
+        line["c3"] = c3
+    if rcm is not None:
+        line["rcm"] = rcm
+        line["rcm_ms"] = rcm["rcm_ms"]
     if world == 1 and not args.no_cpu_baseline:
-        cb = cpu_reference_step(args.cpu_grid)
-        line["cpu_baseline"] = {"value": cb["value"], "unit": "GNNZ/s", "cores": cb["cores"],
-                                "kind": cb["kind"], "sample": cb["sample"],
-                                "rcm_s": cb["rcm_s"], "permute2d_s": cb["permute2d_s"]}
+        cb, _ = cpu_pipeline_step(args.cpu_scale)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample",
+                                                   "coo_to_csr_s", "degree_reorder_s",
+                                                   "permute2d_s")}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

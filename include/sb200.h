@@ -266,6 +266,93 @@ int sb200_degree_rank_combine(int device, int64_t n, const void *row_ptr, const 
                               const void *offset, int64_t flip_from, void *out, int id_type,
                               int nnz_type, void *stream);
 
+
+/* ---- multi-GPU: row-block sharded operators over peer memory ----
+ *
+ * The reference has no distributed code (its "multi-GPU" is the peer copy of
+ * converter/converter_order_two_cuda.cu:41-76).  These are the sharded forms of the operators
+ * above: rank r of `world` owns the contiguous row block
+ * [bounds[r], bounds[r+1]) with a block-local row_ptr and global column ids; results are
+ * bit-identical to the single-GPU operators.  SPMD: every rank makes the same calls with its own
+ * shard.  Every rank owns a WINDOW in its HBM that all peers address directly (CUDA IPC between
+ * processes, peer access inside one process; NVLink / NVSwitch underneath); an exchange is a
+ * kernel that stores straight into the destination rank's window followed by a flag barrier --
+ * counts and offsets never leave the device.  The window must hold the largest exchange of the
+ * operators used: about 2 x (shard bytes) + (n + 1) * sizeof(NNZType) is enough for all of them;
+ * an operator that does not fit fails with SB200_ERR_BAD_ARG and a message giving the size.
+ *
+ *   one process per GPU     sb200_mg_comm_create on every rank, all-gather the 64-byte handles
+ *                           with whatever the application uses (MPI, torch.distributed ...),
+ *                           sb200_mg_comm_connect
+ *   one process, ndev GPUs  sb200_mg_comm_create_local: ndev connected communicators; call the
+ *                           operators from one host thread per GPU (sb200_mg_run_ranks)
+ */
+typedef struct sb200_mg_comm sb200_mg_comm_t;
+int sb200_mg_comm_create(int device, int rank, int world, size_t window_bytes,
+                         sb200_mg_comm_t **out, void *h_out_handle64);
+int sb200_mg_comm_connect(sb200_mg_comm_t *comm, const void *h_all_handles /* world x 64 B */);
+int sb200_mg_comm_create_local(int ndev, const int *devices, size_t window_bytes,
+                               sb200_mg_comm_t **out_comms /* [ndev] */);
+int sb200_mg_comm_destroy(sb200_mg_comm_t *comm);
+int sb200_mg_comm_info(const sb200_mg_comm_t *comm, int *h_rank, int *h_world,
+                       size_t *h_window_bytes);
+/* One process, ndev GPUs: runs fn(rank, user) on one host thread per rank and returns the first
+ * non-zero code (the operators below are collective: every rank must be inside the same call). */
+int sb200_mg_run_ranks(int ndev, int (*fn)(int rank, void *user), void *user);
+/* every rank has reached this point of `stream` and all earlier peer stores are visible */
+int sb200_mg_barrier(sb200_mg_comm_t *comm, void *stream);
+/* h_out[world] = every rank's value.  Synchronises the stream. */
+int sb200_mg_allgather_i64(sb200_mg_comm_t *comm, int64_t value, int64_t *h_out, void *stream);
+
+/* COO -> CSR of this rank's block (all nonzeros of rows [row_lo, row_lo + n_local), (row,col)-
+ * sorted as the COO constructor leaves them): out_row_ptr[n_local+1] block-local, out_col /
+ * out_vals[nnz_local]; h_out2 = {global nnz, nnz of the blocks before this one}.
+ * Synchronises the stream. */
+int sb200_mg_coo_to_csr(sb200_mg_comm_t *comm, int64_t row_lo, int64_t n_local, int64_t m,
+                        int64_t nnz_local, const void *row, const void *col, const void *vals,
+                        void *out_row_ptr, void *out_col, void *out_vals, int64_t *h_out2,
+                        int id_type, int nnz_type, int val_type, void *stream);
+
+/* DegreeReorder of the whole matrix from the block-local row_ptr's: out_inv[n] (the FULL
+ * permutation, inv[old] = new, with the reference's tie rule) on every rank.  h_bounds[world+1]
+ * (host) = the row blocks.  Synchronises the stream. */
+int sb200_mg_degree_reorder(sb200_mg_comm_t *comm, int64_t n, const int64_t *h_bounds,
+                            const void *row_ptr, int ascending, void *out_inv, int id_type,
+                            int nnz_type, void *stream);
+
+/* Permute2D: row_order[n] / col_order[m] are the FULL inverse permutations on every rank (NULL =
+ * identity).  The result is sharded by nnz-balanced blocks of the NEW rows:
+ *   _run    does the work and leaves this rank's new block in its window; h_out_bounds[world+1] =
+ *           the new row blocks, h_out2[3] = {rows, nnz, nnz of the blocks before this one} of
+ *           this rank's block.  Synchronises.
+ *   _fetch  copies the block into out_row_ptr[rows+1] (block-local), out_col / out_vals[nnz] and
+ *           releases the window (val_type / out_vals as in _run). */
+int sb200_mg_permute2d_run(sb200_mg_comm_t *comm, int64_t n, int64_t m, int64_t nnz_total,
+                           const int64_t *h_bounds, const void *row_ptr, const void *col,
+                           const void *vals, const void *row_order, const void *col_order,
+                           int64_t *h_out_bounds, int64_t *h_out2, int id_type, int nnz_type,
+                           int val_type, void *stream);
+int sb200_mg_permute2d_fetch(sb200_mg_comm_t *comm, int64_t n, int64_t new_rows, int64_t new_nnz,
+                             void *out_row_ptr, void *out_col, void *out_vals, int id_type,
+                             int nnz_type, int val_type, void *stream);
+
+/* CSR -> CSC: the result is sharded by nnz-balanced blocks of COLUMNS (col_ptr block-local, row
+ * ids global and ascending inside a column).  _run / _fetch as for Permute2D (h_out2[3] =
+ * {columns, nnz, nnz of the blocks before}); _fetch takes the rank's column block
+ * [col_lo, col_lo + n_cols) = h_out_bounds[rank], h_out2[0] of _run. */
+int sb200_mg_csr_to_csc_run(sb200_mg_comm_t *comm, int64_t n, int64_t m, int64_t nnz_total,
+                            const int64_t *h_bounds, const void *row_ptr, const void *col,
+                            const void *vals, int64_t *h_out_bounds, int64_t *h_out2,
+                            int id_type, int nnz_type, int val_type, void *stream);
+int sb200_mg_csr_to_csc_fetch(sb200_mg_comm_t *comm, int64_t m, int64_t col_lo, int64_t n_cols,
+                              void *out_col_ptr, void *out_row, void *out_vals, int id_type,
+                              int nnz_type, int val_type, void *stream);
+
+/* Permute1D: vals / order / out are this rank's block [h_bounds[rank], h_bounds[rank+1]) of the
+ * arrays; out[order[i]] = vals[i] over the whole array (permute/permute_order_one.cc:17-37). */
+int sb200_mg_permute1d(sb200_mg_comm_t *comm, const int64_t *h_bounds, const void *vals,
+                       const void *order, void *out, int id_type, int val_type, void *stream);
+
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */
 int64_t sb200_launch_count(void);

@@ -1,0 +1,1015 @@
+// mg.cu -- multi-GPU (row-block sharded) operators over peer memory (see mg.cuh).
+//
+// The reference has no distributed code (its whole "multi-GPU" is the peer
+// copy of converter/converter_order_two_cuda.cu:41-76); these are the sharded forms of the same
+// operators: every rank owns a contiguous row block [row_lo, row_lo +
+// n_local) with block-local row_ptr and global column ids, results are bit-identical to the
+// single-GPU operators.  SPMD: every rank calls the same entry point with its own shard
+// (one process per GPU with IPC-connected communicators, or one host thread per GPU inside one
+// process, sb200_mg_comm_create_local).
+//
+//   sb200_mg_coo_to_csr      local COO->CSR of the block + all-gather of the block sizes
+//   sb200_mg_degree_reorder  local rank by degree + per-degree offsets from the gathered degree
+//                            histograms; the full permutation lands on every rank
+//   sb200_mg_permute2d       degrees all-gathered -> new row_ptr (replicated scan) -> every rank
+//                            renumbers / sorts its rows and STORES each into the window of the
+//                            rank that owns the new row, at its final offset
+//   sb200_mg_csr_to_csc      local transpose of the block, column counts reduced through the
+//                            windows, every source stores its column slices into the owner's
+//                            window, the owner interleaves them (source order = row order)
+//   sb200_mg_permute1d       out[order[i]] = vals[i] stored straight into the owner's window
+#include <mutex>
+#include <string>
+#include <thread>
+
+#include "mg.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace sb200 {
+
+// ------------------------------------------------------------------ barrier / small gathers
+// A peer that failed (or never made the matching call) must not hang this GPU: after
+// kMgBarrierTimeoutNs the barrier gives up and raises pad[0] of this rank's control area, which
+// the operators turn into SB200_ERR_INTERNAL at their next synchronisation point.
+constexpr unsigned long long kMgBarrierTimeoutNs = 20ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ unsigned long long mg_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void mg_barrier_kernel(MgPeers p, unsigned long long epoch) {
+  const int r = threadIdx.x;
+  if (r < p.world) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(&p.ctl(r)->flag[p.rank]) = epoch;
+    __threadfence_system();
+    const volatile unsigned long long *mine =
+        reinterpret_cast<const volatile unsigned long long *>(&p.ctl(p.rank)->flag[r]);
+    const unsigned long long t0 = mg_now_ns();
+    while (*mine < epoch) {
+      if (mg_now_ns() - t0 > kMgBarrierTimeoutNs) {
+        p.ctl(p.rank)->pad[0] = 1ull;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+}
+
+// All peer stores issued on `st` before this call are visible to every rank after it (in stream
+// order), and every rank has reached this point.
+void mg_barrier(sb200_mg_comm *c, cudaStream_t st) {
+  c->epoch++;
+  if (c->peers.world == 1) return;
+  SB_LAUNCH(mg_barrier_kernel, 1, 32, 0, st, c->peers, c->epoch);
+}
+
+// table[my rank][slot0 + k] = vals[k] on every rank (k < count)
+__global__ void mg_put_table_kernel(MgPeers p, int slot0, const unsigned long long *__restrict__ vals,
+                                    int count) {
+  const int r = blockIdx.x, k = threadIdx.x;
+  if (r < p.world && k < count) p.ctl(r)->table[p.rank][slot0 + k] = vals[k];
+}
+void mg_put_table(sb200_mg_comm *c, cudaStream_t st, int slot0, const unsigned long long *d_vals,
+                  int count) {
+  SB_REQUIRE(slot0 >= 0 && slot0 + count <= kMgSlots && count <= 64, SB200_ERR_INTERNAL,
+             "table slots out of range");
+  SB_LAUNCH(mg_put_table_kernel, c->peers.world, 64, 0, st, c->peers, slot0, d_vals, count);
+}
+
+// my slice [elems] of bytes-wide elements -> offset `at` of region `region` in EVERY rank's window
+__global__ void __launch_bounds__(256)
+    mg_bcast_slice_kernel(MgPeers p, size_t region, const uint4 *__restrict__ src, size_t at_bytes,
+                          size_t bytes) {
+  // 16-byte words; tails handled by the caller's padding (regions are 256-byte aligned and the
+  // slices are padded to 16 bytes by mg_bcast_slice)
+  const size_t words = bytes / 16;
+  for (int r = blockIdx.y; r < p.world; r += gridDim.y) {
+    uint4 *dst = reinterpret_cast<uint4 *>(p.data(r) + region + at_bytes);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words;
+         i += (size_t)gridDim.x * blockDim.x)
+      dst[i] = src[i];
+  }
+}
+__global__ void mg_bcast_tail_kernel(MgPeers p, size_t region, const char *__restrict__ src,
+                                     size_t at_bytes, size_t from, size_t bytes) {
+  const size_t i = from + threadIdx.x;
+  if (i < bytes)
+    for (int r = 0; r < p.world; r++) (p.data(r) + region + at_bytes)[i] = src[i];
+}
+// (at_bytes must be 16-byte aligned relative to the region when bytes >= 16: callers slice
+// arrays of 4- or 8-byte elements at arbitrary element offsets, so unaligned slices take the
+// byte path)
+void mg_bcast_slice(sb200_mg_comm *c, cudaStream_t st, size_t region, const void *src,
+                    size_t at_bytes, size_t bytes) {
+  if (bytes == 0) return;
+  const bool aligned = (at_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0);
+  if (aligned && bytes >= 16) {
+    const int sms = device_info(c->device).sm_count;
+    dim3 grid((unsigned)(sms * 2 / c->peers.world > 0 ? sms * 2 / c->peers.world : 1),
+              (unsigned)c->peers.world);
+    SB_LAUNCH(mg_bcast_slice_kernel, grid, 256, 0, st, c->peers, region, (const uint4 *)src,
+              at_bytes, bytes);
+    const size_t done = bytes / 16 * 16;
+    if (done < bytes)
+      SB_LAUNCH(mg_bcast_tail_kernel, 1, 16, 0, st, c->peers, region, (const char *)src, at_bytes,
+                done, bytes);
+  } else {
+    for (int r = 0; r < c->peers.world; r++)
+      SB_CUDA(cudaMemcpyAsync(c->peers.data(r) + region + at_bytes, src, bytes,
+                              cudaMemcpyDeviceToDevice, st));
+  }
+}
+
+// after a stream synchronisation: did a barrier of this rank give up?
+static void check_barriers(const sb200_mg_comm *c) {
+  if (c->peers.world == 1) return;
+  unsigned long long failed = 0;
+  SB_CUDA(cudaMemcpy(&failed, &c->peers.ctl(c->peers.rank)->pad[0], sizeof(failed),
+                     cudaMemcpyDeviceToHost));
+  SB_REQUIRE(failed == 0, SB200_ERR_INTERNAL,
+             "multi-GPU barrier timed out: a peer rank failed or did not make the matching call");
+}
+
+// SB200_MG_TRACE=1: per-stage device time of the operators, printed by rank 0 (CUDA events on
+// the operator's stream; the print happens after the operator's own final synchronisation).
+class MgTrace {
+ public:
+  MgTrace(const sb200_mg_comm *c, cudaStream_t st, const char *op)
+      : on_(c->peers.rank == 0 && getenv("SB200_MG_TRACE") != nullptr), st_(st), op_(op) {
+    mark("start");
+  }
+  void mark(const char *name) {
+    if (!on_) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st_);
+    ev_.push_back(e);
+    names_.push_back(name);
+  }
+  ~MgTrace() {
+    if (!on_) return;
+    cudaStreamSynchronize(st_);
+    std::string line = std::string("[mg-trace] ") + op_ + ":";
+    for (size_t i = 1; i < ev_.size(); i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev_[i - 1], ev_[i]);
+      char buf[96];
+      snprintf(buf, sizeof(buf), "  %s=%.3f", names_[i], ms);
+      line += buf;
+    }
+    fprintf(stderr, "%s\n", line.c_str());
+    for (cudaEvent_t e : ev_) cudaEventDestroy(e);
+  }
+
+ private:
+  bool on_;
+  cudaStream_t st_;
+  const char *op_;
+  std::vector<cudaEvent_t> ev_;
+  std::vector<const char *> names_;
+};
+
+static void check_comm(const sb200_mg_comm *c) {
+  SB_REQUIRE(c != nullptr && c->peers.world >= 1 && c->peers.world <= kMgMaxRanks &&
+                 c->peers.rank >= 0 && c->peers.rank < c->peers.world,
+             SB200_ERR_BAD_ARG, "bad communicator");
+  for (int r = 0; r < c->peers.world; r++)
+    SB_REQUIRE(c->peers.win[r] != nullptr, SB200_ERR_BAD_ARG,
+               "communicator not connected (peer %d)", r);
+}
+
+// ------------------------------------------------------------------ Permute1D
+// out[order[i]] = vals[i]: the element goes straight into the window of the rank that owns
+// position order[i] (blocks of `bounds`), then every rank copies its block out.
+template <typename I, typename V>
+__global__ void mg_permute1d_push_kernel(MgPeers p, size_t region, const int64_t *__restrict__ bounds,
+                                         const V *__restrict__ vals, const I *__restrict__ order,
+                                         int64_t n_local) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_local) return;
+  const int64_t j = (int64_t)order[i];
+  int d = 0;
+  while (d + 1 < p.world && j >= bounds[d + 1]) d++;
+  reinterpret_cast<V *>(p.data(d) + region)[j - bounds[d]] = ld_stream(vals + i);
+}
+
+// ------------------------------------------------------------------ DegreeReorder
+// offset[d] = (vertices of smaller degree anywhere) + (same degree in LATER blocks: larger ids
+// rank first, degree_reorder.cc:42-46) - (smaller degree inside this block)
+struct MgHistTotalFn {
+  const unsigned long long *hist;  // [world][nbins] in my window
+  int world;
+  int64_t nbins;
+  __device__ int64_t operator()(int64_t d) const {
+    unsigned long long s = 0;
+    for (int r = 0; r < world; r++) s += hist[(int64_t)r * nbins + d];
+    return (int64_t)s;
+  }
+};
+struct MgHistMineFn {
+  const unsigned long long *hist;
+  int rank;
+  int64_t nbins;
+  __device__ int64_t operator()(int64_t d) const { return (int64_t)hist[(int64_t)rank * nbins + d]; }
+};
+__global__ void mg_degree_offset_kernel(const unsigned long long *__restrict__ hist, int rank,
+                                        int world, int64_t nbins,
+                                        const int64_t *__restrict__ g_start,
+                                        const int64_t *__restrict__ l_start,
+                                        int64_t *__restrict__ offset) {
+  const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= nbins) return;
+  unsigned long long later = 0;
+  for (int r = rank + 1; r < world; r++) later += hist[(int64_t)r * nbins + d];
+  offset[d] = g_start[d] + (int64_t)later - l_start[d];
+}
+
+// ------------------------------------------------------------------ Permute2D
+// replicated: new_deg[row_order[i]] = deg[i]
+template <typename I, typename N>
+__global__ void mg_new_degree_kernel(const N *__restrict__ deg, const I *__restrict__ row_order,
+                                     int64_t n, N *__restrict__ new_deg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) new_deg[row_order ? (int64_t)row_order[i] : i] = deg[i];
+}
+// bounds[k] = first new row whose new_ptr >= k * nnz / world (as sb200_partition_rows)
+template <typename N>
+__global__ void mg_balance_kernel(const N *__restrict__ ptr, int64_t n, int64_t nnz, int parts,
+                                  int64_t *__restrict__ bounds, int64_t *__restrict__ at) {
+  const int k = threadIdx.x;
+  if (k > parts) return;
+  int64_t b;
+  if (k == 0)
+    b = 0;
+  else if (k == parts)
+    b = n;
+  else {
+    const int64_t target = (int64_t)(((__int128)nnz * k) / parts);
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)ptr[mid] < target)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    b = lo;
+  }
+  bounds[k] = b;
+  at[k] = (int64_t)ptr[b];
+}
+// The rows of this rank (already renumbered and sorted in `tcol` / `tval`, laid out by the
+// block-local row_ptr) go into the windows of the ranks that own their new row ids.  One warp
+// per 32 consecutive rows: lane l resolves row l's destination (owner rank + final offset), then
+// the warp walks the rows' concatenated entries 32 at a time -- coalesced reads, and the lanes of
+// one row store a contiguous run.  Rows of kMgLongRow entries or more are left to the LONG
+// variant (one CTA per such row and pass; hubs of a power-law matrix would otherwise keep one
+// warp busy alone).
+constexpr int64_t kMgLongRow = 8192;
+template <typename I, typename N, typename V, bool LONG>
+__global__ void __launch_bounds__(256)
+    mg_push_rows_kernel(MgPeers p, size_t col_region, size_t val_region,
+                        const N *__restrict__ row_ptr, const I *__restrict__ tcol,
+                        const V *__restrict__ tval, const I *__restrict__ row_order, int64_t row_lo,
+                        int64_t n_local, const N *__restrict__ new_ptr,
+                        const int64_t *__restrict__ nb, const int64_t *__restrict__ nb_at,
+                        int64_t *__restrict__ long_list, unsigned *__restrict__ long_count) {
+  // destination of local row i: (pointer to its first column slot, pointer to its first value)
+  auto resolve = [&](int64_t i, I *&oc, V *&ov) {
+    const int64_t j = row_order ? (int64_t)row_order[row_lo + i] : row_lo + i;
+    int d = 0;
+    while (d + 1 < p.world && j >= nb[d + 1]) d++;
+    const int64_t dst = (int64_t)new_ptr[j] - nb_at[d];
+    oc = reinterpret_cast<I *>(p.data(d) + col_region) + dst;
+    ov = has_val<V> ? reinterpret_cast<V *>(p.data(d) + val_region) + dst : nullptr;
+  };
+  if (LONG) {
+    const int64_t count = (int64_t)*long_count;
+    for (int64_t w = blockIdx.x; w < count; w += gridDim.x) {
+      const int64_t i = long_list[w];
+      const int64_t b = (int64_t)row_ptr[i], e = (int64_t)row_ptr[i + 1];
+      I *oc;
+      V *ov;
+      resolve(i, oc, ov);
+      for (int64_t k = threadIdx.x; k < e - b; k += blockDim.x) {
+        oc[k] = ld_stream(tcol + b + k);
+        if constexpr (has_val<V>) {
+          if (tval) ov[k] = ld_stream(tval + b + k);
+        }
+      }
+    }
+    return;
+  }
+  const unsigned lane = lane_id();
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t g = warp * 32; g < n_local; g += nwarps * 32) {
+    const int64_t i = g + lane;
+    int64_t b = 0;
+    unsigned d = 0;
+    I *oc = nullptr;
+    V *ov = nullptr;
+    if (i < n_local) {
+      b = (int64_t)row_ptr[i];
+      const int64_t len = (int64_t)row_ptr[i + 1] - b;
+      if (len >= kMgLongRow) {
+        long_list[atomicAdd(long_count, 1u)] = i;
+      } else if (len > 0) {
+        d = (unsigned)len;
+        resolve(i, oc, ov);
+      }
+    }
+    const unsigned incl = warp_inclusive_scan(d);
+    const unsigned excl = incl - d;
+    const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
+    for (unsigned base = 0; base < tot; base += 32) {
+      const unsigned s = base + lane;
+      unsigned lo = 0;  // number of lanes whose inclusive end <= s == owner lane
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const unsigned val = __shfl_sync(0xffffffffu, incl, (lo + step - 1) & 31);
+        if (val <= s) lo += step;
+      }
+      const unsigned j = lo & 31;
+      const int64_t b_j = __shfl_sync(0xffffffffu, b, j);
+      const unsigned excl_j = __shfl_sync(0xffffffffu, excl, j);
+      const unsigned long long oc_j = __shfl_sync(0xffffffffu, (unsigned long long)oc, j);
+      const unsigned long long ov_j = __shfl_sync(0xffffffffu, (unsigned long long)ov, j);
+      if (s < tot) {
+        const unsigned k = s - excl_j;
+        reinterpret_cast<I *>(oc_j)[k] = ld_stream(tcol + b_j + k);
+        if constexpr (has_val<V>) {
+          if (tval) reinterpret_cast<V *>(ov_j)[k] = ld_stream(tval + b_j + k);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ CSR -> CSC
+// cp[s] = source s's block-local col_ptr over ALL m columns (the CP table in my window)
+template <typename N>
+struct MgColTotalFn {
+  const N *cp;  // [world][m + 1]
+  int world;
+  int64_t m;
+  __device__ N operator()(int64_t c) const {
+    N s = 0;
+    for (int r = 0; r < world; r++) s += cp[(int64_t)r * (m + 1) + c + 1] - cp[(int64_t)r * (m + 1) + c];
+    return s;
+  }
+};
+// Source `rank` stores its slice of columns [cb[d], cb[d+1]) -- rows and values are contiguous in
+// its block-local CSC -- into destination d's staging area, behind the slices of the lower ranks.
+template <typename I, typename N, typename V>
+__global__ void __launch_bounds__(256)
+    mg_push_cols_kernel(MgPeers p, size_t row_region, size_t val_region, const N *__restrict__ cp,
+                        int64_t m, const int64_t *__restrict__ cb, const I *__restrict__ rows,
+                        const V *__restrict__ vals) {
+  const int d = blockIdx.y;
+  const int64_t c0 = cb[d], c1 = cb[d + 1];
+  const N *mine = cp + (int64_t)p.rank * (m + 1);
+  const int64_t from = (int64_t)mine[c0], cnt = (int64_t)mine[c1] - from;
+  int64_t off = 0;
+  for (int r = 0; r < p.rank; r++)
+    off += (int64_t)(cp[(int64_t)r * (m + 1) + c1] - cp[(int64_t)r * (m + 1) + c0]);
+  I *orow = reinterpret_cast<I *>(p.data(d) + row_region) + off;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cnt;
+       k += (int64_t)gridDim.x * blockDim.x)
+    orow[k] = ld_stream(rows + from + k);
+  if constexpr (has_val<V>) {
+    if (vals) {
+      V *oval = reinterpret_cast<V *>(p.data(d) + val_region) + off;
+      for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cnt;
+           k += (int64_t)gridDim.x * blockDim.x)
+        oval[k] = ld_stream(vals + from + k);
+    }
+  }
+}
+// The owner of columns [c0, c1) interleaves the staged slices: inside a column the sources come
+// in rank order, which is ascending row order because the row blocks are ordered.  One lane per
+// column (adjacent lanes read adjacent places of every source's slice and write adjacent
+// segments); columns of kMgLongCol entries or more are done by a whole CTA (LONG = true).
+constexpr int64_t kMgLongCol = 2048;
+template <typename I, typename N, typename V, bool LONG>
+__global__ void __launch_bounds__(256)
+    mg_interleave_kernel(int world, const N *__restrict__ cp, int64_t m, const N *__restrict__ gptr,
+                         int64_t c0, int64_t c1, const I *__restrict__ stg_row,
+                         const V *__restrict__ stg_val, N *__restrict__ out_col_ptr,
+                         I *__restrict__ out_row, V *__restrict__ out_val) {
+  const int64_t g0 = (int64_t)gptr[c0];
+  const int64_t step = LONG ? gridDim.x : (int64_t)gridDim.x * blockDim.x;
+  for (int64_t c = c0 + (LONG ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+       c < c1; c += step) {
+    const int64_t total = (int64_t)gptr[c + 1] - (int64_t)gptr[c];
+    if (!LONG) {
+      out_col_ptr[c - c0] = (N)((int64_t)gptr[c] - g0);
+      if (c == c1 - 1) out_col_ptr[c1 - c0] = (N)((int64_t)gptr[c1] - g0);
+    }
+    if (LONG != (total >= kMgLongCol)) continue;
+    int64_t dst = (int64_t)gptr[c] - g0, stage = 0;
+    for (int r = 0; r < world; r++) {
+      const N *q = cp + (int64_t)r * (m + 1);
+      const int64_t src = stage + ((int64_t)q[c] - (int64_t)q[c0]);
+      const int64_t len = (int64_t)q[c + 1] - (int64_t)q[c];
+      if (LONG) {
+        for (int64_t k = threadIdx.x; k < len; k += blockDim.x) {
+          out_row[dst + k] = stg_row[src + k];
+          if constexpr (has_val<V>) {
+            if (out_val) out_val[dst + k] = stg_val[src + k];
+          }
+        }
+      } else {
+        for (int64_t k = 0; k < len; k++) {
+          out_row[dst + k] = stg_row[src + k];
+          if constexpr (has_val<V>) {
+            if (out_val) out_val[dst + k] = stg_val[src + k];
+          }
+        }
+      }
+      dst += len;
+      stage += (int64_t)q[c1] - (int64_t)q[c0];
+    }
+  }
+}
+template <typename N>
+__global__ void mg_local_ptr_kernel(const N *__restrict__ new_ptr, int64_t lo, int64_t cnt,
+                                    N *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= cnt) out[i] = new_ptr[lo + i] - new_ptr[lo];
+}
+
+}  // namespace sb200
+
+using namespace sb200;
+
+// single-GPU entry points this file builds on
+extern "C" {
+int sb200_coo_to_csr_block(int, int64_t, int64_t, int64_t, int64_t, const void *, const void *,
+                           const void *, void *, void *, void *, int, int, int, void *);
+int sb200_csr_to_csc_block(int, int64_t, int64_t, int64_t, int64_t, const void *, const void *,
+                           const void *, void *, void *, void *, int, int, int, void *);
+int sb200_degree_reorder(int, int64_t, const void *, int, void *, int, int, void *);
+int sb200_degree_histogram(int, int64_t, const void *, int, int64_t, void *, void *);
+int sb200_degree_rank_combine(int, int64_t, const void *, const void *, const void *, int64_t,
+                              void *, int, int, void *);
+int sb200_degrees(int, int64_t, const void *, void *, int, int, void *);
+int sb200_permute2d(int, int64_t, int64_t, int64_t, const void *, const void *, const void *,
+                    const void *, const void *, void *, void *, void *, int, int, int, void *);
+int sb200_max_degree(int, int64_t, const void *, int, int64_t *, void *);
+}
+
+#define SB_RC(expr)                                  \
+  do {                                               \
+    const int rc__ = (expr);                         \
+    if (rc__ != SB200_OK) throw sb200::Error{rc__};  \
+  } while (0)
+
+extern "C" {
+
+// ------------------------------------------------------------------ communicator
+int sb200_mg_comm_create(int device, int rank, int world, size_t window_bytes,
+                         sb200_mg_comm_t **out, void *h_out_handle64) {
+  return guarded(device, [&] {
+    SB_REQUIRE(out && world >= 1 && world <= kMgMaxRanks && rank >= 0 && rank < world,
+               SB200_ERR_BAD_ARG, "bad rank / world (at most %d ranks)", kMgMaxRanks);
+    SB_REQUIRE(window_bytes >= kMgControlBytes + 4096, SB200_ERR_BAD_ARG, "window too small");
+    auto *c = new sb200_mg_comm();
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    c->window_bytes = window_bytes;
+    c->peers.rank = rank;
+    c->peers.world = world;
+    void *w = nullptr;
+    cudaError_t e = cudaMalloc(&w, window_bytes);
+    if (e != cudaSuccess) {
+      delete c;
+      set_error("cudaMalloc of the %zu-byte window failed: %s", window_bytes, cudaGetErrorString(e));
+      throw Error{SB200_ERR_ALLOC};
+    }
+    c->owns_window = true;
+    c->peers.win[rank] = (char *)w;
+    SB_CUDA(cudaMemset(w, 0, kMgControlBytes));
+    SB_CUDA(cudaDeviceSynchronize());
+    if (h_out_handle64) {
+      static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+      cudaIpcMemHandle_t h;
+      if (world > 1)
+        SB_CUDA(cudaIpcGetMemHandle(&h, w));
+      else
+        memset(&h, 0, sizeof(h));
+      memcpy(h_out_handle64, &h, 64);
+    }
+    *out = c;
+  });
+}
+
+int sb200_mg_comm_connect(sb200_mg_comm_t *c, const void *h_all_handles) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  return guarded(c->device, [&] {
+    SB_REQUIRE(h_all_handles || c->peers.world == 1, SB200_ERR_BAD_ARG, "null handles");
+    for (int r = 0; r < c->peers.world; r++) {
+      if (r == c->peers.rank) continue;
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char *)h_all_handles + (size_t)r * 64, 64);
+      void *p = nullptr;
+      SB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      c->peers.win[r] = (char *)p;
+    }
+    c->ipc = true;
+  });
+}
+
+int sb200_mg_comm_create_local(int ndev, const int *devices, size_t window_bytes,
+                               sb200_mg_comm_t **out_comms) {
+  if (!devices || !out_comms || ndev < 1 || ndev > kMgMaxRanks) return SB200_ERR_BAD_ARG;
+  for (int r = 0; r < ndev; r++) out_comms[r] = nullptr;
+  for (int r = 0; r < ndev; r++) {
+    const int rc = sb200_mg_comm_create(devices[r], r, ndev, window_bytes, &out_comms[r], nullptr);
+    if (rc != SB200_OK) return rc;
+  }
+  for (int r = 0; r < ndev; r++) {
+    const int rc = guarded(devices[r], [&] {
+      for (int q = 0; q < ndev; q++) {
+        if (q == r) continue;
+        if (devices[q] != devices[r]) {
+          int can = 0;
+          SB_CUDA(cudaDeviceCanAccessPeer(&can, devices[r], devices[q]));
+          SB_REQUIRE(can, SB200_ERR_BAD_DEVICE, "device %d cannot access device %d", devices[r],
+                     devices[q]);
+          cudaError_t e = cudaDeviceEnablePeerAccess(devices[q], 0);
+          if (e == cudaErrorPeerAccessAlreadyEnabled)
+            cudaGetLastError();
+          else
+            SB_CUDA(e);
+        }
+        out_comms[r]->peers.win[q] = out_comms[q]->peers.win[q];
+      }
+    });
+    if (rc != SB200_OK) return rc;
+  }
+  return SB200_OK;
+}
+
+int sb200_mg_comm_destroy(sb200_mg_comm_t *c) {
+  if (!c) return SB200_OK;
+  return guarded(c->device, [&] {
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->peers.world; r++) {
+      if (r == c->peers.rank || !c->peers.win[r]) continue;
+      if (c->ipc) cudaIpcCloseMemHandle(c->peers.win[r]);
+    }
+    if (c->owns_window && c->peers.win[c->peers.rank]) cudaFree(c->peers.win[c->peers.rank]);
+    cudaGetLastError();
+    delete c;
+  });
+}
+
+int sb200_mg_comm_info(const sb200_mg_comm_t *c, int *h_rank, int *h_world, size_t *h_window_bytes) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  if (h_rank) *h_rank = c->peers.rank;
+  if (h_world) *h_world = c->peers.world;
+  if (h_window_bytes) *h_window_bytes = c->window_bytes;
+  return SB200_OK;
+}
+
+// One process, ndev GPUs: fn(rank, user) on one host thread per rank (the operators are
+// collective: every rank has to be inside the same call at the same time).  Returns the first
+// non-zero code any rank returned.
+int sb200_mg_run_ranks(int ndev, int (*fn)(int rank, void *user), void *user) {
+  if (ndev < 1 || ndev > kMgMaxRanks || !fn) return SB200_ERR_BAD_ARG;
+  std::vector<int> rc(ndev, SB200_OK);
+  std::vector<std::thread> th;
+  th.reserve(ndev);
+  for (int r = 0; r < ndev; r++) th.emplace_back([&, r] { rc[r] = fn(r, user); });
+  for (auto &t : th) t.join();
+  for (int r = 0; r < ndev; r++)
+    if (rc[r] != SB200_OK) return rc[r];
+  return SB200_OK;
+}
+
+int sb200_mg_barrier(sb200_mg_comm_t *c, void *stream) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  return guarded(c->device, [&] {
+    check_comm(c);
+    mg_barrier(c, (cudaStream_t)stream);
+  });
+}
+
+// h_out[world] = every rank's value (a collective; synchronises the stream)
+int sb200_mg_allgather_i64(sb200_mg_comm_t *c, int64_t value, int64_t *h_out, void *stream) {
+  if (!c || !h_out) return SB200_ERR_BAD_ARG;
+  return guarded(c->device, [&] {
+    check_comm(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace ws(c->device, st);
+    unsigned long long *d = ws.alloc<unsigned long long>(1);
+    const unsigned long long v = (unsigned long long)value;
+    SB_CUDA(cudaMemcpyAsync(d, &v, sizeof(v), cudaMemcpyHostToDevice, st));
+    mg_barrier(c, st);  // nobody still reads slot 0 of an earlier gather
+    mg_put_table(c, st, 0, d, 1);
+    mg_barrier(c, st);
+    MgControl *ctl = c->peers.ctl(c->peers.rank);
+    for (int r = 0; r < c->peers.world; r++)
+      SB_CUDA(cudaMemcpyAsync(&h_out[r], &ctl->table[r][0], sizeof(int64_t),
+                              cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    check_barriers(c);
+  });
+}
+
+// ------------------------------------------------------------------ COO -> CSR
+// The block's COO (all nonzeros of rows [row_lo, row_lo + n_local), (row, col)-sorted as the COO
+// constructor leaves them) -> block-local CSR; h_out2 = {global nnz, nnz of the blocks before
+// this one}.  Synchronises the stream (to return the totals).
+int sb200_mg_coo_to_csr(sb200_mg_comm_t *c, int64_t row_lo, int64_t n_local, int64_t m,
+                        int64_t nnz_local, const void *row, const void *col, const void *vals,
+                        void *out_row_ptr, void *out_col, void *out_vals, int64_t *h_out2,
+                        int id_type, int nnz_type, int val_type, void *stream) {
+  if (!c || !h_out2) return SB200_ERR_BAD_ARG;
+  return guarded(c->device, [&] {
+    check_comm(c);
+    SB_RC(sb200_coo_to_csr_block(c->device, row_lo, n_local, m, nnz_local, row, col, vals,
+                                 out_row_ptr, out_col, out_vals, id_type, nnz_type, val_type,
+                                 stream));
+    std::vector<int64_t> all(c->peers.world);
+    SB_RC(sb200_mg_allgather_i64(c, nnz_local, all.data(), stream));
+    int64_t total = 0, base = 0;
+    for (int r = 0; r < c->peers.world; r++) {
+      total += all[r];
+      if (r < c->peers.rank) base += all[r];
+    }
+    h_out2[0] = total;
+    h_out2[1] = base;
+  });
+}
+
+// ------------------------------------------------------------------ Permute1D
+// vals / order: this rank's block [bounds[rank], bounds[rank+1]) of the arrays; out: the same
+// block of the result out[order[i]] = vals[i].  h_bounds: world+1 block boundaries (host).
+int sb200_mg_permute1d(sb200_mg_comm_t *c, const int64_t *h_bounds, const void *vals,
+                       const void *order, void *out, int id_type, int val_type, void *stream) {
+  if (!c || !h_bounds) return SB200_ERR_BAD_ARG;
+  return guarded(c->device, [&] {
+    check_comm(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int world = c->peers.world, rank = c->peers.rank;
+    const int64_t n_local = h_bounds[rank + 1] - h_bounds[rank];
+    const int vb = dtype_size(val_type);
+    SB_REQUIRE(vb == 4 || vb == 8, SB200_ERR_BAD_DTYPE, "val_type %d unsupported", val_type);
+    int64_t largest = 0;
+    for (int r = 0; r < world; r++)
+      largest = std::max(largest, h_bounds[r + 1] - h_bounds[r]);
+    MgLayout lay(c);
+    const size_t region = lay.take((size_t)largest * vb);
+    Workspace ws(c->device, st);
+    int64_t *d_bounds = ws.alloc<int64_t>(world + 1);
+    SB_CUDA(cudaMemcpyAsync(d_bounds, h_bounds, (world + 1) * sizeof(int64_t),
+                            cudaMemcpyHostToDevice, st));
+    mg_barrier(c, st);  // the region is free on every rank
+    if (n_local > 0) {
+      dispatch_id(id_type, [&](auto I_) {
+        using I = decltype(I_);
+        const unsigned grid = (unsigned)ceil_div(n_local, 256);
+        if (vb == 4)
+          SB_LAUNCH((mg_permute1d_push_kernel<I, uint32_t>), grid, 256, 0, st, c->peers, region,
+                    (const int64_t *)d_bounds, (const uint32_t *)vals, (const I *)order, n_local);
+        else
+          SB_LAUNCH((mg_permute1d_push_kernel<I, uint64_t>), grid, 256, 0, st, c->peers, region,
+                    (const int64_t *)d_bounds, (const uint64_t *)vals, (const I *)order, n_local);
+      });
+    }
+    mg_barrier(c, st);
+    if (n_local > 0)
+      SB_CUDA(cudaMemcpyAsync(out, c->peers.data(rank) + region, (size_t)n_local * vb,
+                              cudaMemcpyDeviceToDevice, st));
+    mg_barrier(c, st);  // nobody overwrites the region before it has been copied out
+  });
+}
+
+// ------------------------------------------------------------------ DegreeReorder
+// row_ptr: block-local row_ptr of rows [h_bounds[rank], h_bounds[rank+1]); out_inv[n]: the FULL
+// permutation (inv[old] = new) on every rank.  Synchronises the stream once (largest degree).
+int sb200_mg_degree_reorder(sb200_mg_comm_t *c, int64_t n, const int64_t *h_bounds,
+                            const void *row_ptr, int ascending, void *out_inv, int id_type,
+                            int nnz_type, void *stream) {
+  if (!c || !h_bounds) return SB200_ERR_BAD_ARG;
+  return guarded(c->device, [&] {
+    check_comm(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int world = c->peers.world, rank = c->peers.rank;
+    const int64_t lo = h_bounds[rank], nl = h_bounds[rank + 1] - lo;
+    const int ib = dtype_size(id_type);
+    SB_REQUIRE(ib == 4 || ib == 8, SB200_ERR_BAD_DTYPE, "bad id_type");
+    Workspace ws(c->device, st);
+    // block-local order (degree ascending, id descending)
+    void *local = ws.alloc_bytes((size_t)(nl > 0 ? nl : 1) * ib);
+    SB_RC(sb200_degree_reorder(c->device, nl, row_ptr, 1, local, id_type, nnz_type, stream));
+    // largest degree anywhere
+    int64_t my_max = 0;
+    SB_RC(sb200_max_degree(c->device, nl, row_ptr, nnz_type, &my_max, stream));
+    std::vector<int64_t> all(world);
+    SB_RC(sb200_mg_allgather_i64(c, my_max, all.data(), stream));
+    int64_t maxdeg = 0;
+    for (int r = 0; r < world; r++) maxdeg = std::max(maxdeg, all[r]);
+    const int64_t nbins = maxdeg + 1;
+    MgLayout lay(c);
+    const size_t hist_region = lay.take((size_t)world * nbins * sizeof(unsigned long long));
+    const size_t inv_region = lay.take((size_t)n * ib);
+    unsigned long long *hist = ws.alloc<unsigned long long>(nbins);
+    SB_RC(sb200_degree_histogram(c->device, nl, row_ptr, nnz_type, nbins, hist, stream));
+    mg_barrier(c, st);
+    mg_bcast_slice(c, st, hist_region, hist, (size_t)rank * nbins * sizeof(unsigned long long),
+                   (size_t)nbins * sizeof(unsigned long long));
+    mg_barrier(c, st);
+    const unsigned long long *all_hist =
+        reinterpret_cast<const unsigned long long *>(c->peers.data(rank) + hist_region);
+    int64_t *g_start = ws.alloc<int64_t>(nbins + 1), *l_start = ws.alloc<int64_t>(nbins + 1);
+    int64_t *offset = ws.alloc<int64_t>(nbins);
+    exclusive_scan<int64_t>(ws, MgHistTotalFn{all_hist, world, nbins}, g_start, nbins);
+    exclusive_scan<int64_t>(ws, MgHistMineFn{all_hist, rank, nbins}, l_start, nbins);
+    SB_LAUNCH(mg_degree_offset_kernel, (unsigned)ceil_div(nbins, 256), 256, 0, st, all_hist, rank,
+              world, nbins, (const int64_t *)g_start, (const int64_t *)l_start, offset);
+    void *part = ws.alloc_bytes((size_t)(nl > 0 ? nl : 1) * ib);
+    SB_RC(sb200_degree_rank_combine(c->device, nl, row_ptr, local, offset,
+                                    ascending ? -1 : n - 1, part, id_type, nnz_type, stream));
+    mg_bcast_slice(c, st, inv_region, part, (size_t)lo * ib, (size_t)nl * ib);
+    mg_barrier(c, st);
+    SB_CUDA(cudaMemcpyAsync(out_inv, c->peers.data(rank) + inv_region, (size_t)n * ib,
+                            cudaMemcpyDeviceToDevice, st));
+    mg_barrier(c, st);
+  });
+}
+
+// ------------------------------------------------------------------ Permute2D
+// Input: block-local CSR of rows [h_bounds[rank], h_bounds[rank+1]) + the FULL inverse
+// permutations (replicated; NULL = identity).  The result is sharded by nnz-balanced blocks of
+// the NEW rows.  Two calls:
+//   sb200_mg_permute2d_run    does all the work; the permuted block is left in this rank's window.
+//                             h_out_bounds[world+1] = the new row blocks, h_out2[3] = {rows, nnz,
+//                             nnz of the blocks before} of this rank's new block.  Synchronises.
+//   sb200_mg_permute2d_fetch  copies the block out of the window (row_ptr block-local) and
+//                             releases the window for the next operator.
+int sb200_mg_permute2d_run(sb200_mg_comm_t *c, int64_t n, int64_t m, int64_t nnz_total,
+                           const int64_t *h_bounds, const void *row_ptr, const void *col,
+                           const void *vals, const void *row_order, const void *col_order,
+                           int64_t *h_out_bounds, int64_t *h_out2, int id_type, int nnz_type,
+                           int val_type, void *stream) {
+  if (!c || !h_bounds || !h_out_bounds || !h_out2) return SB200_ERR_BAD_ARG;
+  return guarded(c->device, [&] {
+    check_comm(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int world = c->peers.world, rank = c->peers.rank;
+    const int64_t lo = h_bounds[rank], nl = h_bounds[rank + 1] - lo;
+    const bool hv = vals != nullptr && val_type != SB200_VOID;
+    dispatch_inv(id_type, nnz_type, val_type, hv, [&](auto I_, auto N_, auto V_) {
+      using I = decltype(I_);
+      using N = decltype(N_);
+      using V = decltype(V_);
+      Workspace ws(c->device, st);
+      MgTrace tr(c, st, "permute2d_run");
+      MgLayout lay(c);
+      const size_t deg_region = lay.take((size_t)(n + 1) * sizeof(N));
+      // (the received block: nnz-balanced, so about nnz_total / world entries plus a row of
+      // slack per boundary; it gets what is left of the window)
+      const size_t left = c->window_bytes - kMgControlBytes - lay.used();
+      SB_REQUIRE(left > 4096, SB200_ERR_BAD_ARG, "multi-GPU window too small");
+      const size_t room = (left - 1024) / (sizeof(I) + (has_val<V> ? sizeof(V) : 0));
+      const size_t col_region = lay.take(room * sizeof(I));
+      const size_t val_region = has_val<V> ? lay.take(room * sizeof(V)) : 0;
+      // ---- every row's degree, everywhere
+      N *deg_local = ws.alloc<N>(nl > 0 ? nl : 1);
+      SB_RC(sb200_degrees(c->device, nl, row_ptr, deg_local, nnz_type, nnz_type, stream));
+      mg_barrier(c, st);  // the window is free on every rank
+      mg_bcast_slice(c, st, deg_region, deg_local, (size_t)lo * sizeof(N), (size_t)nl * sizeof(N));
+      mg_barrier(c, st);
+      tr.mark("degrees_allgather");
+      const N *deg = reinterpret_cast<const N *>(c->peers.data(rank) + deg_region);
+      // ---- replicated: degrees in the new order, new row_ptr, nnz-balanced new row blocks
+      N *new_deg = ws.alloc<N>(n > 0 ? n : 1), *new_ptr = ws.alloc<N>(n + 1);
+      if (n > 0)
+        SB_LAUNCH((mg_new_degree_kernel<I, N>), (unsigned)ceil_div(n, 256), 256, 0, st, deg,
+                  (const I *)row_order, n, new_deg);
+      exclusive_scan<N>(ws, LoadFn<N>{new_deg}, new_ptr, n);
+      int64_t *nb = ws.alloc<int64_t>(world + 1), *nb_at = ws.alloc<int64_t>(world + 1);
+      SB_LAUNCH((mg_balance_kernel<N>), 1, 32, 0, st, (const N *)new_ptr, n, nnz_total, world, nb,
+                nb_at);
+      // ---- my rows: renumber the columns and sort every row (rows stay in their old order)
+      N h_nnz_local = 0;
+      SB_CUDA(cudaMemcpyAsync(&h_nnz_local, (const N *)row_ptr + nl, sizeof(N),
+                              cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaMemcpyAsync(h_out_bounds, nb, (world + 1) * sizeof(int64_t),
+                              cudaMemcpyDeviceToHost, st));
+      std::vector<int64_t> h_at(world + 1);
+      SB_CUDA(cudaMemcpyAsync(h_at.data(), nb_at, (world + 1) * sizeof(int64_t),
+                              cudaMemcpyDeviceToHost, st));
+      tr.mark("new_ptr_and_blocks");
+      SB_CUDA(cudaStreamSynchronize(st));
+      const int64_t my_nnz = (int64_t)h_nnz_local;
+      const int64_t new_rows = h_out_bounds[rank + 1] - h_out_bounds[rank];
+      const int64_t new_nnz = h_at[rank + 1] - h_at[rank];
+      SB_REQUIRE((size_t)new_nnz <= room, SB200_ERR_BAD_ARG,
+                 "multi-GPU window too small for the permuted block (%lld entries, room for %zu)",
+                 (long long)new_nnz, room);
+      N *t_ptr = ws.alloc<N>(nl + 1);
+      I *t_col = ws.alloc<I>(my_nnz > 0 ? my_nnz : 1);
+      V *t_val = nullptr;
+      if constexpr (has_val<V>) t_val = ws.alloc<V>(my_nnz > 0 ? my_nnz : 1);
+      SB_RC(sb200_permute2d(c->device, nl, m, my_nnz, row_ptr, col, hv ? vals : nullptr, nullptr,
+                            col_order, t_ptr, t_col, t_val, id_type, nnz_type,
+                            hv ? val_type : SB200_VOID, stream));
+      tr.mark("local_renumber_sort");
+      // ---- every row goes to its final place in the owner's window
+      if (nl > 0 && my_nnz > 0) {
+        const int sms = device_info(c->device).sm_count;
+        const int64_t warps = std::min<int64_t>(ceil_div(nl, 32), (int64_t)sms * 64);
+        int64_t *long_list = ws.alloc<int64_t>(my_nnz / kMgLongRow + 1);
+        unsigned *long_count = ws.alloc<unsigned>(1);
+        SB_CUDA(cudaMemsetAsync(long_count, 0, sizeof(unsigned), st));
+        SB_LAUNCH((mg_push_rows_kernel<I, N, V, false>), (unsigned)ceil_div(warps * 32, 256), 256,
+                  0, st, c->peers, col_region, val_region, (const N *)t_ptr, (const I *)t_col,
+                  (const V *)t_val, (const I *)row_order, lo, nl, (const N *)new_ptr,
+                  (const int64_t *)nb, (const int64_t *)nb_at, long_list, long_count);
+        SB_LAUNCH((mg_push_rows_kernel<I, N, V, true>), sms * 2, 256, 0, st, c->peers, col_region,
+                  val_region, (const N *)t_ptr, (const I *)t_col, (const V *)t_val,
+                  (const I *)row_order, lo, nl, (const N *)new_ptr, (const int64_t *)nb,
+                  (const int64_t *)nb_at, long_list, long_count);
+      }
+      tr.mark("push_rows");
+      mg_barrier(c, st);
+      tr.mark("barrier");
+      // the new block's row_ptr waits in the (now unused) degree region of my own window
+      N *keep = reinterpret_cast<N *>(c->peers.data(rank) + deg_region);
+      SB_LAUNCH((mg_local_ptr_kernel<N>), (unsigned)ceil_div(new_rows + 1, 256), 256, 0, st,
+                (const N *)new_ptr, h_out_bounds[rank], new_rows, keep);
+      SB_CUDA(cudaStreamSynchronize(st));
+      check_barriers(c);
+      h_out2[0] = new_rows;
+      h_out2[1] = new_nnz;
+      h_out2[2] = h_at[rank];
+    });
+  });
+}
+
+int sb200_mg_permute2d_fetch(sb200_mg_comm_t *c, int64_t n, int64_t new_rows, int64_t new_nnz,
+                             void *out_row_ptr, void *out_col, void *out_vals, int id_type,
+                             int nnz_type, int val_type, void *stream) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  return guarded(c->device, [&] {
+    check_comm(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rank = c->peers.rank;
+    const bool hv = out_vals != nullptr && val_type != SB200_VOID;
+    const size_t ib = dtype_size(id_type), nb = dtype_size(nnz_type), vb = dtype_size(val_type);
+    // the same carving as sb200_mg_permute2d_run
+    MgLayout lay(c);
+    const size_t deg_region = lay.take((size_t)(n + 1) * nb);
+    const size_t left = c->window_bytes - kMgControlBytes - lay.used();
+    const size_t room = (left - 1024) / (ib + (hv ? vb : 0));
+    const size_t col_region = lay.take(room * ib);
+    const size_t val_region = hv ? lay.take(room * vb) : 0;
+    char *mine = c->peers.data(rank);
+    SB_CUDA(cudaMemcpyAsync(out_row_ptr, mine + deg_region, (size_t)(new_rows + 1) * nb,
+                            cudaMemcpyDeviceToDevice, st));
+    if (new_nnz > 0) {
+      SB_CUDA(cudaMemcpyAsync(out_col, mine + col_region, (size_t)new_nnz * ib,
+                              cudaMemcpyDeviceToDevice, st));
+      if (hv)
+        SB_CUDA(cudaMemcpyAsync(out_vals, mine + val_region, (size_t)new_nnz * vb,
+                                cudaMemcpyDeviceToDevice, st));
+    }
+    mg_barrier(c, st);  // the window may be reused once every rank has copied its block out
+  });
+}
+
+// ------------------------------------------------------------------ CSR -> CSC
+// Input: block-local CSR of rows [h_bounds[rank], h_bounds[rank+1]).  The result is sharded by
+// nnz-balanced blocks of COLUMNS.  Two calls, as for Permute2D:
+//   sb200_mg_csr_to_csc_run    local transpose of the block, col_ptr tables all-gathered through
+//                              the windows, column slices stored into their owners' windows.
+//                              h_out_bounds[world+1] = the column blocks, h_out2[3] = {columns,
+//                              nnz, nnz of the blocks before} of this rank's block.  Synchronises.
+//   sb200_mg_csr_to_csc_fetch  interleaves the staged slices into the caller's arrays
+//                              (col_ptr block-local, rows global ids, ascending inside a column).
+int sb200_mg_csr_to_csc_run(sb200_mg_comm_t *c, int64_t n, int64_t m, int64_t nnz_total,
+                            const int64_t *h_bounds, const void *row_ptr, const void *col,
+                            const void *vals, int64_t *h_out_bounds, int64_t *h_out2,
+                            int id_type, int nnz_type, int val_type, void *stream) {
+  if (!c || !h_bounds || !h_out_bounds || !h_out2) return SB200_ERR_BAD_ARG;
+  return guarded(c->device, [&] {
+    check_comm(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int world = c->peers.world, rank = c->peers.rank;
+    const int64_t lo = h_bounds[rank], nl = h_bounds[rank + 1] - lo;
+    const bool hv = vals != nullptr && val_type != SB200_VOID;
+    dispatch_inv(id_type, nnz_type, val_type, hv, [&](auto I_, auto N_, auto V_) {
+      using I = decltype(I_);
+      using N = decltype(N_);
+      using V = decltype(V_);
+      Workspace ws(c->device, st);
+      MgTrace tr(c, st, "csr_to_csc_run");
+      MgLayout lay(c);
+      const size_t cp_region = lay.take((size_t)world * (m + 1) * sizeof(N));
+      const size_t gptr_region = lay.take((size_t)(m + 1) * sizeof(N));
+      const size_t left = c->window_bytes - kMgControlBytes - lay.used();
+      SB_REQUIRE(left > 4096, SB200_ERR_BAD_ARG, "multi-GPU window too small");
+      const size_t room = (left - 1024) / (sizeof(I) + (has_val<V> ? sizeof(V) : 0));
+      const size_t row_region = lay.take(room * sizeof(I));
+      const size_t val_region = has_val<V> ? lay.take(room * sizeof(V)) : 0;
+      // ---- local transpose of the block (rows ascending inside a column, global row ids)
+      N h_nnz_local = 0;
+      SB_CUDA(cudaMemcpyAsync(&h_nnz_local, (const N *)row_ptr + nl, sizeof(N),
+                              cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaStreamSynchronize(st));
+      const int64_t my_nnz = (int64_t)h_nnz_local;
+      N *cp = ws.alloc<N>(m + 1);
+      I *rows = ws.alloc<I>(my_nnz > 0 ? my_nnz : 1);
+      V *tv = nullptr;
+      if constexpr (has_val<V>) tv = ws.alloc<V>(my_nnz > 0 ? my_nnz : 1);
+      SB_RC(sb200_csr_to_csc_block(c->device, lo, nl, m, my_nnz, row_ptr, col,
+                                   hv ? vals : nullptr, cp, rows, tv, id_type, nnz_type,
+                                   hv ? val_type : SB200_VOID, stream));
+      tr.mark("local_transpose");
+      // ---- every rank's col_ptr table, everywhere
+      mg_barrier(c, st);  // the window is free on every rank
+      mg_bcast_slice(c, st, cp_region, cp, (size_t)rank * (m + 1) * sizeof(N),
+                     (size_t)(m + 1) * sizeof(N));
+      mg_barrier(c, st);
+      tr.mark("col_ptr_allgather");
+      const N *all_cp = reinterpret_cast<const N *>(c->peers.data(rank) + cp_region);
+      N *gptr = reinterpret_cast<N *>(c->peers.data(rank) + gptr_region);
+      exclusive_scan<N>(ws, MgColTotalFn<N>{all_cp, world, m}, gptr, m);
+      int64_t *cb = ws.alloc<int64_t>(world + 1), *cb_at = ws.alloc<int64_t>(world + 1);
+      SB_LAUNCH((mg_balance_kernel<N>), 1, 32, 0, st, (const N *)gptr, m, nnz_total, world, cb,
+                cb_at);
+      tr.mark("global_ptr_and_blocks");
+      // ---- my slice of every destination's columns, into its staging area
+      if (my_nnz > 0) {
+        dim3 grid((unsigned)std::max(1, device_info(c->device).sm_count * 4 / world),
+                  (unsigned)world);
+        SB_LAUNCH((mg_push_cols_kernel<I, N, V>), grid, 256, 0, st, c->peers, row_region,
+                  val_region, all_cp, m, (const int64_t *)cb, (const I *)rows, (const V *)tv);
+      }
+      tr.mark("push_cols");
+      mg_barrier(c, st);
+      tr.mark("barrier");
+      std::vector<int64_t> h_at(world + 1);
+      SB_CUDA(cudaMemcpyAsync(h_out_bounds, cb, (world + 1) * sizeof(int64_t),
+                              cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaMemcpyAsync(h_at.data(), cb_at, (world + 1) * sizeof(int64_t),
+                              cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaStreamSynchronize(st));
+      check_barriers(c);
+      h_out2[0] = h_out_bounds[rank + 1] - h_out_bounds[rank];
+      h_out2[1] = h_at[rank + 1] - h_at[rank];
+      h_out2[2] = h_at[rank];
+      SB_REQUIRE((size_t)h_out2[1] <= room, SB200_ERR_BAD_ARG,
+                 "multi-GPU window too small for the transposed block (%lld entries, room for %zu)",
+                 (long long)h_out2[1], room);
+    });
+  });
+}
+
+int sb200_mg_csr_to_csc_fetch(sb200_mg_comm_t *c, int64_t m, int64_t col_lo, int64_t n_cols,
+                              void *out_col_ptr, void *out_row, void *out_vals, int id_type,
+                              int nnz_type, int val_type, void *stream) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  return guarded(c->device, [&] {
+    check_comm(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int world = c->peers.world, rank = c->peers.rank;
+    const bool hv = out_vals != nullptr && val_type != SB200_VOID;
+    dispatch_inv(id_type, nnz_type, val_type, hv, [&](auto I_, auto N_, auto V_) {
+      using I = decltype(I_);
+      using N = decltype(N_);
+      using V = decltype(V_);
+      MgLayout lay(c);  // the same carving as sb200_mg_csr_to_csc_run
+      const size_t cp_region = lay.take((size_t)world * (m + 1) * sizeof(N));
+      const size_t gptr_region = lay.take((size_t)(m + 1) * sizeof(N));
+      const size_t left = c->window_bytes - kMgControlBytes - lay.used();
+      const size_t room = (left - 1024) / (sizeof(I) + (has_val<V> ? sizeof(V) : 0));
+      const size_t row_region = lay.take(room * sizeof(I));
+      const size_t val_region = has_val<V> ? lay.take(room * sizeof(V)) : 0;
+      char *mine = c->peers.data(rank);
+      const N *all_cp = reinterpret_cast<const N *>(mine + cp_region);
+      const N *gptr = reinterpret_cast<const N *>(mine + gptr_region);
+      if (n_cols > 0) {
+        const int sms = device_info(c->device).sm_count;
+        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n_cols, 256), (int64_t)sms * 16);
+        SB_LAUNCH((mg_interleave_kernel<I, N, V, false>), grid, 256, 0, st, world, all_cp, m, gptr,
+                  col_lo, col_lo + n_cols, (const I *)(mine + row_region),
+                  (const V *)(mine + val_region), (N *)out_col_ptr, (I *)out_row, (V *)out_vals);
+        SB_LAUNCH((mg_interleave_kernel<I, N, V, true>), sms * 4, 256, 0, st, world, all_cp, m,
+                  gptr, col_lo, col_lo + n_cols, (const I *)(mine + row_region),
+                  (const V *)(mine + val_region), (N *)out_col_ptr, (I *)out_row, (V *)out_vals);
+      } else {
+        SB_CUDA(cudaMemsetAsync(out_col_ptr, 0, sizeof(N), st));
+      }
+      mg_barrier(c, st);  // the window may be reused once every rank is done with its staging
+    });
+  });
+}
+
+}  // extern "C"

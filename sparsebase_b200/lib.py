@@ -31,6 +31,11 @@ SYMBOLS = [
     "sb200_reset_launch_count", "sb200_coo_to_csr_block", "sb200_csr_to_csc_block",
     "sb200_exclusive_scan", "sb200_rank_keys", "sb200_max_degree", "sb200_degree_histogram",
     "sb200_degree_rank_combine",
+    "sb200_mg_comm_create", "sb200_mg_comm_connect", "sb200_mg_comm_create_local",
+    "sb200_mg_comm_destroy", "sb200_mg_comm_info", "sb200_mg_run_ranks", "sb200_mg_barrier", "sb200_mg_allgather_i64",
+    "sb200_mg_coo_to_csr", "sb200_mg_degree_reorder", "sb200_mg_permute2d_run",
+    "sb200_mg_permute2d_fetch", "sb200_mg_csr_to_csc_run", "sb200_mg_csr_to_csc_fetch",
+    "sb200_mg_permute1d",
 ]
 
 

@@ -90,3 +90,41 @@ def test_sharded_operators_nccl(graph, scale):
            str(scale)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "SHARDED OK" in r.stdout, r.stdout[-3000:] + r.stderr[-5000:]
+
+
+@pytest.mark.parametrize("graph,scale", [("rmat", 15), ("er", 16)])
+def test_peer_memory_operators(graph, scale):
+    """The sb200_mg_* operators (peer-memory windows, CUDA IPC between the ranks) bit-equal to the
+    single-GPU operators: tests/mg_gpu_worker.py under torchrun."""
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    world = 2 if ngpu < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29541",
+           os.path.join(ROOT, "tests", "mg_gpu_worker.py"), "--graph", graph, "--scale",
+           str(scale)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MG OK" in r.stdout, r.stdout[-3000:] + r.stderr[-5000:]
+
+
+def test_peer_memory_single_rank(sb):
+    """world = 1: the same entry points degenerate to the local operators (no window traffic)."""
+    from sparsebase_b200 import mg
+    n, r, c = graphs.rmat(11, 8, seed=31)
+    vals = graphs.vals_for(len(r), seed=2)
+    comm = mg.Comm(64 << 20)
+    s = mg.coo_to_csr(comm, n, n, [0, n], dev(r), dev(c), dev(vals))
+    g = sb.coo_to_csr(n, n, dev(r), dev(c), dev(vals))
+    assert torch.equal(s.row_ptr, g[0]) and torch.equal(s.col, g[1]) and torch.equal(s.vals, g[2])
+    inv = mg.degree_reorder(comm, s, True)
+    assert torch.equal(inv, sb.degree_reorder(n, g[0], True))
+    p = mg.permute2d(comm, s, inv, inv)
+    e = sb.permute2d(n, n, g[0], g[1], g[2], inv, inv)
+    assert torch.equal(p.row_ptr, e[0]) and torch.equal(p.col, e[1]) and torch.equal(p.vals, e[2])
+    t = mg.csr_to_csc(comm, s)
+    e = sb.csr_to_csc(n, n, g[0], g[1], g[2])
+    assert torch.equal(t.col_ptr, e[0]) and torch.equal(t.row, e[1]) and torch.equal(t.vals, e[2])
+    x = dev(graphs.vals_for(n, seed=4))
+    assert torch.equal(mg.permute1d(comm, [0, n], x, inv), sb.permute1d(x, inv))
+    comm.destroy()
