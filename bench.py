@@ -94,7 +94,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -404,13 +404,15 @@ def main():
             record[3].record()
         return inv, (p.bounds[rank], p.bounds[rank + 1]), (p.row_ptr, p.col, p.vals)
 
+    # (clocks are sampled every 20 ms from the warm-up steps on -- the same load -- so that a
+    # timed region of a few tens of milliseconds at 8 GPUs still has samples)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(W):
         step()
     # ---- device-resident timing: K steps, CUDA events on the launching stream
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     lib.reset_launch_count()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):

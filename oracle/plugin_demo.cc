@@ -212,6 +212,8 @@ int main() {
   auto conv = converter::ConverterStore::GetStore()
                   .get_converter<converter::ConverterOrderTwo<I, N, V>>();
   sb200_plugin::RegisterConversions<I, N, V>(*conv);
+  // CSR <-> CUDACSR through the plugin's staged transfers instead of the reference's own
+  sb200_plugin::RegisterTransfers<I, N, V>(*conv);
 
   run_case("grid 61x47", grid(61, 47), cpu, gpu);
   run_case("grid 300x200", grid(300, 200), cpu, gpu);

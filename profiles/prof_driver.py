@@ -17,6 +17,7 @@ ap.add_argument("--ops", default="permute2d,csr_to_csc,coo_to_csr,degree_reorder
 ap.add_argument("--grid", type=int, default=4096)
 ap.add_argument("--graph", default="poisson")
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--perm", default="random", help="random | degree (DegreeReorder of the matrix)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 if args.graph == "poisson":
@@ -35,6 +36,8 @@ row = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int32),
 g = torch.Generator(device=dev)
 g.manual_seed(1)
 perm = torch.randperm(n, generator=g, device=dev).to(torch.int32)
+if args.perm == "degree":
+    perm = lib.degree_reorder(n, rp, True)
 ops = args.ops.split(",")
 for _ in range(args.reps):
     if "rcm" in ops:

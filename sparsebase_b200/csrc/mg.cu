@@ -226,6 +226,8 @@ __global__ void mg_degree_offset_kernel(const unsigned long long *__restrict__ h
   offset[d] = g_start[d] + (int64_t)later - l_start[d];
 }
 
+constexpr int64_t kMgChunk = 4096;  // entries per work item of the chunked copies
+
 // ------------------------------------------------------------------ Permute2D
 // replicated: new_deg[row_order[i]] = deg[i]
 template <typename I, typename N>
@@ -261,89 +263,86 @@ __global__ void mg_balance_kernel(const N *__restrict__ ptr, int64_t n, int64_t 
   at[k] = (int64_t)ptr[b];
 }
 // The rows of this rank (already renumbered and sorted in `tcol` / `tval`, laid out by the
-// block-local row_ptr) go into the windows of the ranks that own their new row ids.  One warp
-// per 32 consecutive rows: lane l resolves row l's destination (owner rank + final offset), then
-// the warp walks the rows' concatenated entries 32 at a time -- coalesced reads, and the lanes of
-// one row store a contiguous run.  Rows of kMgLongRow entries or more are left to the LONG
-// variant (one CTA per such row and pass; hubs of a power-law matrix would otherwise keep one
-// warp busy alone).
-constexpr int64_t kMgLongRow = 8192;
-template <typename I, typename N, typename V, bool LONG>
+// block-local row_ptr) go into the windows of the ranks that own their new row ids.
+// Balanced over ENTRIES, not rows (the heavy rows of a power-law matrix sit next to each other:
+// with one warp per 32 rows ncu showed 11 % of the warps active): every warp takes kMgPushChunk
+// consecutive entries, finds the row holding the first one by binary search, and walks the rows
+// from there -- lane l resolves row l's destination (owner rank + final offset, clipped to the
+// chunk), then the warp moves the rows' concatenated entries 32 at a time: coalesced reads, and
+// the lanes of one row store a contiguous run.  A hub row simply spans many chunks.
+constexpr int64_t kMgPushChunk = 4096;
+template <typename I, typename N, typename V>
 __global__ void __launch_bounds__(256)
     mg_push_rows_kernel(MgPeers p, size_t col_region, size_t val_region,
                         const N *__restrict__ row_ptr, const I *__restrict__ tcol,
                         const V *__restrict__ tval, const I *__restrict__ row_order, int64_t row_lo,
-                        int64_t n_local, const N *__restrict__ new_ptr,
-                        const int64_t *__restrict__ nb, const int64_t *__restrict__ nb_at,
-                        int64_t *__restrict__ long_list, unsigned *__restrict__ long_count) {
-  // destination of local row i: (pointer to its first column slot, pointer to its first value)
-  auto resolve = [&](int64_t i, I *&oc, V *&ov) {
-    const int64_t j = row_order ? (int64_t)row_order[row_lo + i] : row_lo + i;
-    int d = 0;
-    while (d + 1 < p.world && j >= nb[d + 1]) d++;
-    const int64_t dst = (int64_t)new_ptr[j] - nb_at[d];
-    oc = reinterpret_cast<I *>(p.data(d) + col_region) + dst;
-    ov = has_val<V> ? reinterpret_cast<V *>(p.data(d) + val_region) + dst : nullptr;
-  };
-  if (LONG) {
-    const int64_t count = (int64_t)*long_count;
-    for (int64_t w = blockIdx.x; w < count; w += gridDim.x) {
-      const int64_t i = long_list[w];
-      const int64_t b = (int64_t)row_ptr[i], e = (int64_t)row_ptr[i + 1];
-      I *oc;
-      V *ov;
-      resolve(i, oc, ov);
-      for (int64_t k = threadIdx.x; k < e - b; k += blockDim.x) {
-        oc[k] = ld_stream(tcol + b + k);
-        if constexpr (has_val<V>) {
-          if (tval) ov[k] = ld_stream(tval + b + k);
-        }
-      }
-    }
-    return;
-  }
+                        int64_t n_local, int64_t nnz_local, const N *__restrict__ new_ptr,
+                        const int64_t *__restrict__ nb, const int64_t *__restrict__ nb_at) {
   const unsigned lane = lane_id();
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t g = warp * 32; g < n_local; g += nwarps * 32) {
-    const int64_t i = g + lane;
-    int64_t b = 0;
-    unsigned d = 0;
-    I *oc = nullptr;
-    V *ov = nullptr;
-    if (i < n_local) {
-      b = (int64_t)row_ptr[i];
-      const int64_t len = (int64_t)row_ptr[i + 1] - b;
-      if (len >= kMgLongRow) {
-        long_list[atomicAdd(long_count, 1u)] = i;
-      } else if (len > 0) {
-        d = (unsigned)len;
-        resolve(i, oc, ov);
-      }
+  const int64_t nchunks = (nnz_local + kMgPushChunk - 1) / kMgPushChunk;
+  for (int64_t w = warp; w < nchunks; w += nwarps) {
+    const int64_t e0 = w * kMgPushChunk;
+    const int64_t e1 = e0 + kMgPushChunk < nnz_local ? e0 + kMgPushChunk : nnz_local;
+    int64_t lo = 0, hi = n_local;  // last row with row_ptr[row] <= e0
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)row_ptr[mid] <= e0)
+        lo = mid;
+      else
+        hi = mid;
     }
-    const unsigned incl = warp_inclusive_scan(d);
-    const unsigned excl = incl - d;
-    const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
-    for (unsigned base = 0; base < tot; base += 32) {
-      const unsigned s = base + lane;
-      unsigned lo = 0;  // number of lanes whose inclusive end <= s == owner lane
-#pragma unroll
-      for (int step = 16; step > 0; step >>= 1) {
-        const unsigned val = __shfl_sync(0xffffffffu, incl, (lo + step - 1) & 31);
-        if (val <= s) lo += step;
-      }
-      const unsigned j = lo & 31;
-      const int64_t b_j = __shfl_sync(0xffffffffu, b, j);
-      const unsigned excl_j = __shfl_sync(0xffffffffu, excl, j);
-      const unsigned long long oc_j = __shfl_sync(0xffffffffu, (unsigned long long)oc, j);
-      const unsigned long long ov_j = __shfl_sync(0xffffffffu, (unsigned long long)ov, j);
-      if (s < tot) {
-        const unsigned k = s - excl_j;
-        reinterpret_cast<I *>(oc_j)[k] = ld_stream(tcol + b_j + k);
-        if constexpr (has_val<V>) {
-          if (tval) reinterpret_cast<V *>(ov_j)[k] = ld_stream(tval + b_j + k);
+    for (int64_t g = lo; g < n_local; g += 32) {
+      const int64_t i = g + lane;
+      int64_t b = 0;
+      unsigned d = 0;
+      I *oc = nullptr;
+      V *ov = nullptr;
+      int64_t row_begin = nnz_local;  // (rows past the end start beyond every chunk)
+      if (i < n_local) {
+        row_begin = (int64_t)row_ptr[i];
+        const int64_t row_end = (int64_t)row_ptr[i + 1];
+        b = row_begin > e0 ? row_begin : e0;
+        const int64_t e = row_end < e1 ? row_end : e1;
+        if (e > b) {
+          // destination: the owner of the new row id, at the row's final offset in its block
+          const int64_t j = row_order ? (int64_t)row_order[row_lo + i] : row_lo + i;
+          int r = 0;
+          while (r + 1 < p.world && j >= nb[r + 1]) r++;
+          const int64_t dst = (int64_t)new_ptr[j] - nb_at[r] + (b - row_begin);
+          oc = reinterpret_cast<I *>(p.data(r) + col_region) + dst;
+          if constexpr (has_val<V>) ov = reinterpret_cast<V *>(p.data(r) + val_region) + dst;
+          d = (unsigned)(e - b);
         }
       }
+      const unsigned incl = warp_inclusive_scan(d);
+      const unsigned excl = incl - d;
+      const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
+      for (unsigned base = 0; base < tot; base += 32) {
+        const unsigned s = base + lane;
+        unsigned own = 0;  // number of lanes whose inclusive end <= s == owner lane
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const unsigned val = __shfl_sync(0xffffffffu, incl, (own + step - 1) & 31);
+          if (val <= s) own += step;
+        }
+        const unsigned j = own & 31;
+        const int64_t b_j = __shfl_sync(0xffffffffu, b, j);
+        const unsigned excl_j = __shfl_sync(0xffffffffu, excl, j);
+        const unsigned long long oc_j = __shfl_sync(0xffffffffu, (unsigned long long)oc, j);
+        const unsigned long long ov_j = __shfl_sync(0xffffffffu, (unsigned long long)ov, j);
+        if (s < tot) {
+          const unsigned k = s - excl_j;
+          reinterpret_cast<I *>(oc_j)[k] = ld_stream(tcol + b_j + k);
+          if constexpr (has_val<V>) {
+            if (tval) reinterpret_cast<V *>(ov_j)[k] = ld_stream(tval + b_j + k);
+          }
+        }
+      }
+      // the next 32 rows start at or beyond the end of the chunk: done
+      if (__shfl_sync(0xffffffffu, i + 1 < n_local ? (int64_t)row_ptr[i + 1] : nnz_local, 31) >= e1)
+        break;
     }
   }
 }
@@ -391,42 +390,36 @@ __global__ void __launch_bounds__(256)
 // The owner of columns [c0, c1) interleaves the staged slices: inside a column the sources come
 // in rank order, which is ascending row order because the row blocks are ordered.  One lane per
 // column (adjacent lanes read adjacent places of every source's slice and write adjacent
-// segments); columns of kMgLongCol entries or more are done by a whole CTA (LONG = true).
-constexpr int64_t kMgLongCol = 2048;
-template <typename I, typename N, typename V, bool LONG>
+// segments); columns of kMgLongCol entries or more go to a list and mg_interleave_long_kernel
+// copies them in chunks dealt out over the whole grid -- a power-law matrix has columns of
+// millions of entries, and its heavy columns sit next to each other.
+constexpr int64_t kMgLongCol = 64;
+template <typename I, typename N, typename V>
 __global__ void __launch_bounds__(256)
     mg_interleave_kernel(int world, const N *__restrict__ cp, int64_t m, const N *__restrict__ gptr,
                          int64_t c0, int64_t c1, const I *__restrict__ stg_row,
                          const V *__restrict__ stg_val, N *__restrict__ out_col_ptr,
-                         I *__restrict__ out_row, V *__restrict__ out_val) {
+                         I *__restrict__ out_row, V *__restrict__ out_val,
+                         int64_t *__restrict__ long_list, unsigned *__restrict__ long_count) {
   const int64_t g0 = (int64_t)gptr[c0];
-  const int64_t step = LONG ? gridDim.x : (int64_t)gridDim.x * blockDim.x;
-  for (int64_t c = c0 + (LONG ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
-       c < c1; c += step) {
+  for (int64_t c = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < c1;
+       c += (int64_t)gridDim.x * blockDim.x) {
     const int64_t total = (int64_t)gptr[c + 1] - (int64_t)gptr[c];
-    if (!LONG) {
-      out_col_ptr[c - c0] = (N)((int64_t)gptr[c] - g0);
-      if (c == c1 - 1) out_col_ptr[c1 - c0] = (N)((int64_t)gptr[c1] - g0);
+    out_col_ptr[c - c0] = (N)((int64_t)gptr[c] - g0);
+    if (c == c1 - 1) out_col_ptr[c1 - c0] = (N)((int64_t)gptr[c1] - g0);
+    if (total >= kMgLongCol) {
+      long_list[atomicAdd(long_count, 1u)] = c;
+      continue;
     }
-    if (LONG != (total >= kMgLongCol)) continue;
     int64_t dst = (int64_t)gptr[c] - g0, stage = 0;
     for (int r = 0; r < world; r++) {
       const N *q = cp + (int64_t)r * (m + 1);
       const int64_t src = stage + ((int64_t)q[c] - (int64_t)q[c0]);
       const int64_t len = (int64_t)q[c + 1] - (int64_t)q[c];
-      if (LONG) {
-        for (int64_t k = threadIdx.x; k < len; k += blockDim.x) {
-          out_row[dst + k] = stg_row[src + k];
-          if constexpr (has_val<V>) {
-            if (out_val) out_val[dst + k] = stg_val[src + k];
-          }
-        }
-      } else {
-        for (int64_t k = 0; k < len; k++) {
-          out_row[dst + k] = stg_row[src + k];
-          if constexpr (has_val<V>) {
-            if (out_val) out_val[dst + k] = stg_val[src + k];
-          }
+      for (int64_t k = 0; k < len; k++) {
+        out_row[dst + k] = stg_row[src + k];
+        if constexpr (has_val<V>) {
+          if (out_val) out_val[dst + k] = stg_val[src + k];
         }
       }
       dst += len;
@@ -434,6 +427,70 @@ __global__ void __launch_bounds__(256)
     }
   }
 }
+template <typename N>
+struct MgColChunksFn {  // chunks of long column k of the list
+  const int64_t *list;
+  const unsigned *count;
+  const N *gptr;
+  __device__ int64_t operator()(int64_t k) const {
+    if (k >= (int64_t)*count) return 0;
+    const int64_t c = list[k];
+    return ((int64_t)gptr[c + 1] - (int64_t)gptr[c] + kMgChunk - 1) / kMgChunk;
+  }
+};
+// One CTA per chunk of kMgChunk output entries of a long column: the chunk's sources are
+// resolved from the column's per-source counts (shared memory), every thread copies entries.
+template <typename I, typename N, typename V>
+__global__ void __launch_bounds__(256)
+    mg_interleave_long_kernel(int world, const N *__restrict__ cp, int64_t m,
+                              const N *__restrict__ gptr, int64_t c0, int64_t c1,
+                              const I *__restrict__ stg_row, const V *__restrict__ stg_val,
+                              I *__restrict__ out_row, V *__restrict__ out_val,
+                              const int64_t *__restrict__ long_list,
+                              const unsigned *__restrict__ long_count,
+                              const int64_t *__restrict__ first_chunk) {
+  __shared__ int64_t s_src[kMgMaxRanks], s_end[kMgMaxRanks + 1];
+  const int64_t nlong = (int64_t)*long_count;
+  if (nlong == 0) return;
+  const int64_t nchunks = first_chunk[nlong];
+  const int64_t g0 = (int64_t)gptr[c0];
+  for (int64_t w = blockIdx.x; w < nchunks; w += gridDim.x) {
+    int64_t lo = 0, hi = nlong;  // last list entry with first_chunk <= w
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (first_chunk[mid] <= w)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    const int64_t c = long_list[lo];
+    __syncthreads();
+    if (threadIdx.x == 0) {  // per source: where its piece starts in staging / ends in the column
+      int64_t stage = 0, run = 0;
+      for (int r = 0; r < world; r++) {
+        const N *q = cp + (int64_t)r * (m + 1);
+        s_src[r] = stage + ((int64_t)q[c] - (int64_t)q[c0]) - run;  // + position in column
+        run += (int64_t)q[c + 1] - (int64_t)q[c];
+        s_end[r] = run;
+        stage += (int64_t)q[c1] - (int64_t)q[c0];
+      }
+    }
+    __syncthreads();
+    const int64_t total = (int64_t)gptr[c + 1] - (int64_t)gptr[c];
+    const int64_t k0 = (w - first_chunk[lo]) * kMgChunk;
+    const int64_t k1 = k0 + kMgChunk < total ? k0 + kMgChunk : total;
+    const int64_t dst = (int64_t)gptr[c] - g0;
+    for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+      int r = 0;
+      while (r + 1 < world && k >= s_end[r]) r++;
+      out_row[dst + k] = ld_stream(stg_row + s_src[r] + k);
+      if constexpr (has_val<V>) {
+        if (out_val) out_val[dst + k] = ld_stream(stg_val + s_src[r] + k);
+      }
+    }
+  }
+}
+
 template <typename N>
 __global__ void mg_local_ptr_kernel(const N *__restrict__ new_ptr, int64_t lo, int64_t cnt,
                                     N *__restrict__ out) {
@@ -824,18 +881,12 @@ int sb200_mg_permute2d_run(sb200_mg_comm_t *c, int64_t n, int64_t m, int64_t nnz
       // ---- every row goes to its final place in the owner's window
       if (nl > 0 && my_nnz > 0) {
         const int sms = device_info(c->device).sm_count;
-        const int64_t warps = std::min<int64_t>(ceil_div(nl, 32), (int64_t)sms * 64);
-        int64_t *long_list = ws.alloc<int64_t>(my_nnz / kMgLongRow + 1);
-        unsigned *long_count = ws.alloc<unsigned>(1);
-        SB_CUDA(cudaMemsetAsync(long_count, 0, sizeof(unsigned), st));
-        SB_LAUNCH((mg_push_rows_kernel<I, N, V, false>), (unsigned)ceil_div(warps * 32, 256), 256,
-                  0, st, c->peers, col_region, val_region, (const N *)t_ptr, (const I *)t_col,
-                  (const V *)t_val, (const I *)row_order, lo, nl, (const N *)new_ptr,
-                  (const int64_t *)nb, (const int64_t *)nb_at, long_list, long_count);
-        SB_LAUNCH((mg_push_rows_kernel<I, N, V, true>), sms * 2, 256, 0, st, c->peers, col_region,
-                  val_region, (const N *)t_ptr, (const I *)t_col, (const V *)t_val,
-                  (const I *)row_order, lo, nl, (const N *)new_ptr, (const int64_t *)nb,
-                  (const int64_t *)nb_at, long_list, long_count);
+        const int64_t warps =
+            std::min<int64_t>(ceil_div(my_nnz, kMgPushChunk), (int64_t)sms * 64);
+        SB_LAUNCH((mg_push_rows_kernel<I, N, V>), (unsigned)ceil_div(warps * 32, 256), 256, 0, st,
+                  c->peers, col_region, val_region, (const N *)t_ptr, (const I *)t_col,
+                  (const V *)t_val, (const I *)row_order, lo, nl, my_nnz, (const N *)new_ptr,
+                  (const int64_t *)nb, (const int64_t *)nb_at);
       }
       tr.mark("push_rows");
       mg_barrier(c, st);
@@ -997,13 +1048,32 @@ int sb200_mg_csr_to_csc_fetch(sb200_mg_comm_t *c, int64_t m, int64_t col_lo, int
       const N *gptr = reinterpret_cast<const N *>(mine + gptr_region);
       if (n_cols > 0) {
         const int sms = device_info(c->device).sm_count;
+        Workspace ws(c->device, st);
+        MgTrace tr(c, st, "csr_to_csc_fetch");
+        // (a long column has >= kMgLongCol entries, so there are at most nnz / kMgLongCol)
+        N h_ends[2] = {0, 0};  // the block's nnz bounds the number of long columns in it
+        SB_CUDA(cudaMemcpyAsync(&h_ends[0], gptr + col_lo, sizeof(N), cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaMemcpyAsync(&h_ends[1], gptr + col_lo + n_cols, sizeof(N),
+                                cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        const int64_t long_cap = (int64_t)(h_ends[1] - h_ends[0]) / kMgLongCol + 1;
+        int64_t *long_list = ws.alloc<int64_t>(long_cap);
+        unsigned *long_count = ws.alloc<unsigned>(1);
+        SB_CUDA(cudaMemsetAsync(long_count, 0, sizeof(unsigned), st));
         const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n_cols, 256), (int64_t)sms * 16);
-        SB_LAUNCH((mg_interleave_kernel<I, N, V, false>), grid, 256, 0, st, world, all_cp, m, gptr,
+        SB_LAUNCH((mg_interleave_kernel<I, N, V>), grid, 256, 0, st, world, all_cp, m, gptr, col_lo,
+                  col_lo + n_cols, (const I *)(mine + row_region), (const V *)(mine + val_region),
+                  (N *)out_col_ptr, (I *)out_row, (V *)out_vals, long_list, long_count);
+        tr.mark("interleave_short");
+        int64_t *first_chunk = ws.alloc<int64_t>(long_cap + 1);
+        exclusive_scan<int64_t>(ws, MgColChunksFn<N>{long_list, long_count, gptr}, first_chunk,
+                                long_cap);
+        SB_LAUNCH((mg_interleave_long_kernel<I, N, V>), sms * 8, 256, 0, st, world, all_cp, m, gptr,
                   col_lo, col_lo + n_cols, (const I *)(mine + row_region),
-                  (const V *)(mine + val_region), (N *)out_col_ptr, (I *)out_row, (V *)out_vals);
-        SB_LAUNCH((mg_interleave_kernel<I, N, V, true>), sms * 4, 256, 0, st, world, all_cp, m,
-                  gptr, col_lo, col_lo + n_cols, (const I *)(mine + row_region),
-                  (const V *)(mine + val_region), (N *)out_col_ptr, (I *)out_row, (V *)out_vals);
+                  (const V *)(mine + val_region), (I *)out_row, (V *)out_vals,
+                  (const int64_t *)long_list, (const unsigned *)long_count,
+                  (const int64_t *)first_chunk);
+        tr.mark("interleave_long");
       } else {
         SB_CUDA(cudaMemsetAsync(out_col_ptr, 0, sizeof(N), st));
       }

@@ -9,7 +9,11 @@
 //       COO  -> CUDACSR   H2D of the (constructed, sorted) COO + sb200_coo_to_csr
 //       CUDACSR -> CSC    sb200_csr_to_csc on the device + D2H       (to_context = CPU)
 //       CUDACSR -> COO    sb200_csr_to_coo on the device + D2H       (to_context = CPU)
-//     (CSR <-> CUDACSR and CUDACSR -> CUDACSR are SparseBase's own cudaMemcpy functions.)
+//   sb200_plugin::RegisterTransfers(converter)            replaces SparseBase's own blocking,
+//       pageable cudaMemcpy functions for CSR <-> CUDACSR and CUDACSR -> CUDACSR (peer) by staged
+//       transfers (two pinned buffers filled / drained by all host threads while the previous
+//       chunk is on the bus); they also keep the column count m and size row_ptr with n + 1
+//       entries (converter_order_two_cuda.cu:37-38, :55-57 lose m and under-allocate).
 //   sb200_plugin::Register(DegreeReorder&) / (RCMReorder&) / (PermuteOrderTwo&) /
 //                 (PermuteOrderOne&) / (DegreeDistribution&) / (Degrees&)
 //     FunctionMatcherMixin::RegisterFunction({CUDACSR id} or {CUDAArray id}, fn) -- the pattern
@@ -22,6 +26,7 @@
 // INTEGRATION.md shows the ten-line change a maintainer would make to register these by
 // default (inside ConverterOrderTwo::ResetConverterOrderTwo and the operators' constructors).
 #pragma once
+#include <cstring>
 #include <stdexcept>
 #include <string>
 
@@ -66,17 +71,102 @@ inline void check(int rc, int device) {
 
 template <typename T>
 constexpr int dtype_of() {
-  if constexpr (std::is_void_v<T>)
+  if constexpr (std::is_void_v<T>) {
     return SB200_VOID;
-  else if constexpr (std::is_same_v<T, float>)
-    return SB200_F32;
-  else if constexpr (std::is_same_v<T, double>)
-    return SB200_F64;
-  else if constexpr (sizeof(T) == 4)
-    return std::is_signed_v<T> ? SB200_I32 : SB200_U32;
-  else
-    return std::is_signed_v<T> ? SB200_I64 : SB200_U64;
+  } else {
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8,
+                  "libsb200 moves 4- and 8-byte index / value types only");
+    if constexpr (std::is_same_v<T, float>)
+      return SB200_F32;
+    else if constexpr (std::is_same_v<T, double>)
+      return SB200_F64;
+    else if constexpr (sizeof(T) == 4)
+      return std::is_signed_v<T> ? SB200_I32 : SB200_U32;
+    else
+      return std::is_signed_v<T> ? SB200_I64 : SB200_U64;
+  }
 }
+
+// ------------------------------------------------------------------ staged transfers
+// SparseBase's host arrays are pageable (new[]).  A plain cudaMemcpy of pageable memory runs at
+// a fraction of the PCIe rate; here every transfer goes through two pinned buffers: all host
+// threads copy chunk k+1 between the user's array and a pinned buffer while chunk k is on the
+// bus.  One Stager per device and thread; sync() once after the last array of a call.
+class Stager {
+ public:
+  static Stager &get(int dev) {
+    static thread_local Stager *per_dev[64] = {nullptr};
+    if (dev < 0 || dev >= 64) throw Error(SB200_ERR_BAD_DEVICE, "device out of range");
+    if (!per_dev[dev]) per_dev[dev] = new Stager(dev);
+    return *per_dev[dev];
+  }
+  void h2d(void *dst, const void *src, size_t bytes) {
+    select();
+    for (size_t off = 0; off < bytes; off += kChunk) {
+      const size_t len = bytes - off < kChunk ? bytes - off : kChunk;
+      const int k = turn_++ & 1;
+      cuda(cudaEventSynchronize(ev_[k]));
+      host_copy(buf_[k], (const char *)src + off, len);
+      cuda(cudaMemcpyAsync((char *)dst + off, buf_[k], len, cudaMemcpyHostToDevice, st_));
+      cuda(cudaEventRecord(ev_[k], st_));
+    }
+  }
+  void d2h(void *dst, const void *src, size_t bytes) {
+    select();
+    size_t pend_off[2] = {0, 0}, pend_len[2] = {0, 0};
+    for (size_t off = 0; off < bytes; off += kChunk) {
+      const size_t len = bytes - off < kChunk ? bytes - off : kChunk;
+      const int k = turn_++ & 1;
+      drain(dst, k, pend_off, pend_len);  // the buffer's previous chunk goes to the user first
+      cuda(cudaMemcpyAsync(buf_[k], (const char *)src + off, len, cudaMemcpyDeviceToHost, st_));
+      cuda(cudaEventRecord(ev_[k], st_));
+      pend_off[k] = off;
+      pend_len[k] = len;
+    }
+    drain(dst, turn_ & 1, pend_off, pend_len);
+    drain(dst, (turn_ + 1) & 1, pend_off, pend_len);
+  }
+  void sync() {
+    select();
+    cuda(cudaStreamSynchronize(st_));
+  }
+  void *stream() const { return st_; }
+
+ private:
+  static constexpr size_t kChunk = 16u << 20;
+  explicit Stager(int dev) : dev_(dev) {
+    select();
+    cuda(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+      cuda(cudaMallocHost(&buf_[k], kChunk));
+      cuda(cudaEventCreateWithFlags(&ev_[k], cudaEventDisableTiming));
+    }
+  }
+  void select() { cuda(cudaSetDevice(dev_)); }
+  void cuda(cudaError_t e) {
+    if (e != cudaSuccess) throw Error(SB200_ERR_CUDA, cudaGetErrorString(e));
+  }
+  void drain(void *dst, int k, size_t *off, size_t *len) {
+    if (!len[k]) return;
+    cuda(cudaEventSynchronize(ev_[k]));
+    host_copy((char *)dst + off[k], buf_[k], len[k]);
+    len[k] = 0;
+  }
+  static void host_copy(void *dst, const void *src, size_t bytes) {
+    constexpr size_t kPiece = 1u << 20;
+    const long pieces = (long)((bytes + kPiece - 1) / kPiece);
+#pragma omp parallel for schedule(static)
+    for (long p = 0; p < pieces; p++) {
+      const size_t at = (size_t)p * kPiece, len = bytes - at < kPiece ? bytes - at : kPiece;
+      std::memcpy((char *)dst + at, (const char *)src + at, len);
+    }
+  }
+  int dev_;
+  cudaStream_t st_ = nullptr;
+  void *buf_[2] = {nullptr, nullptr};
+  cudaEvent_t ev_[2] = {nullptr, nullptr};
+  unsigned turn_ = 0;
+};
 
 template <typename T>
 T *dev_alloc(int dev, size_t count) {
@@ -95,8 +185,8 @@ T *to_device(int dev, const T *h, size_t count) {
   } else {
     if (!h) return nullptr;
     T *d = dev_alloc<T>(dev, count);
-    check(sb200_memcpy_h2d(dev, d, h, count * sizeof(T), nullptr), dev);
-    check(sb200_stream_synchronize(dev, nullptr), dev);
+    Stager::get(dev).h2d(d, h, count * sizeof(T));
+    Stager::get(dev).sync();  // (the kernels run on the default stream)
     return d;
   }
 }
@@ -107,8 +197,9 @@ T *to_host(int dev, const T *d, size_t count) {
   } else {
     if (!d) return nullptr;
     T *h = new T[count ? count : 1];
-    check(sb200_memcpy_d2h(dev, h, d, count * sizeof(T), nullptr), dev);
-    check(sb200_stream_synchronize(dev, nullptr), dev);
+    check(sb200_stream_synchronize(dev, nullptr), dev);  // the producer ran on the default stream
+    Stager::get(dev).d2h(h, d, count * sizeof(T));
+    Stager::get(dev).sync();
     return h;
   }
 }
@@ -133,8 +224,79 @@ sbase::format::Format *CooCUDACsr(sbase::format::Format *source, sbase::context:
                                   dtype_of<I>(), dtype_of<N>(), dtype_of<V>(), nullptr);
   sb200_stream_synchronize(dev, nullptr);
   dev_free(dev, row), dev_free(dev, col), dev_free(dev, vals);
+  if (rc != SB200_OK) dev_free(dev, o_ptr), dev_free(dev, o_col), dev_free(dev, o_val);
   check(rc, dev);
   return new sbase::format::CUDACSR<I, N, V>(dims[0], dims[1], nnz, o_ptr, o_col, o_val, *ctx,
+                                             sbase::format::kOwned);
+}
+
+// ---- CSR <-> CUDACSR and CUDACSR -> CUDACSR (peer): staged transfers that keep m and move the
+//      n + 1 row pointers (replacing converter_order_two_cuda.cu:11-105)
+template <typename I, typename N, typename V>
+sbase::format::Format *CsrCUDACsr(sbase::format::Format *source, sbase::context::Context *to) {
+  auto *csr = source->AsAbsolute<sbase::format::CSR<I, N, V>>();
+  auto *ctx = static_cast<sbase::context::CUDAContext *>(to);
+  const int dev = ctx->device_id;
+  const auto dims = csr->get_dimensions();
+  const size_t nnz = csr->get_num_nnz();
+  N *d_ptr = dev_alloc<N>(dev, dims[0] + 1);
+  I *d_col = dev_alloc<I>(dev, nnz);
+  V *d_val = csr->get_vals() ? dev_alloc<V>(dev, nnz) : nullptr;
+  Stager &sg = Stager::get(dev);
+  sg.h2d(d_ptr, csr->get_row_ptr(), (dims[0] + 1) * sizeof(N));
+  sg.h2d(d_col, csr->get_col(), nnz * sizeof(I));
+  if constexpr (!std::is_void_v<V>) {
+    if (d_val) sg.h2d(d_val, csr->get_vals(), nnz * sizeof(V));
+  }
+  sg.sync();
+  return new sbase::format::CUDACSR<I, N, V>(dims[0], dims[1], nnz, d_ptr, d_col, d_val, *ctx,
+                                             sbase::format::kOwned);
+}
+template <typename I, typename N, typename V>
+sbase::format::Format *CUDACsrCsr(sbase::format::Format *source, sbase::context::Context *) {
+  auto *csr = source->AsAbsolute<sbase::format::CUDACSR<I, N, V>>();
+  const int dev = csr->get_cuda_context()->device_id;
+  const auto dims = csr->get_dimensions();
+  const size_t nnz = csr->get_num_nnz();
+  N *h_ptr = new N[dims[0] + 1];
+  I *h_col = new I[nnz ? nnz : 1];
+  check(sb200_stream_synchronize(dev, nullptr), dev);
+  Stager &sg = Stager::get(dev);
+  sg.d2h(h_ptr, csr->get_row_ptr(), (dims[0] + 1) * sizeof(N));
+  sg.d2h(h_col, csr->get_col(), nnz * sizeof(I));
+  V *h_val = nullptr;
+  if constexpr (!std::is_void_v<V>) {
+    if (csr->get_vals()) {
+      h_val = new V[nnz ? nnz : 1];
+      sg.d2h(h_val, csr->get_vals(), nnz * sizeof(V));
+    }
+  }
+  sg.sync();
+  return new sbase::format::CSR<I, N, V>(dims[0], dims[1], h_ptr, h_col, h_val,
+                                         sbase::format::kOwned, /*ignore_sort=*/true);
+}
+template <typename I, typename N, typename V>
+sbase::format::Format *CUDACsrCUDACsr(sbase::format::Format *source, sbase::context::Context *to) {
+  auto *csr = source->AsAbsolute<sbase::format::CUDACSR<I, N, V>>();
+  auto *ctx = static_cast<sbase::context::CUDAContext *>(to);
+  const int src_dev = csr->get_cuda_context()->device_id, dev = ctx->device_id;
+  const auto dims = csr->get_dimensions();
+  const size_t nnz = csr->get_num_nnz();
+  N *d_ptr = dev_alloc<N>(dev, dims[0] + 1);
+  I *d_col = dev_alloc<I>(dev, nnz);
+  V *d_val = csr->get_vals() ? dev_alloc<V>(dev, nnz) : nullptr;
+  int rc = sb200_memcpy_d2d(dev, d_ptr, src_dev, csr->get_row_ptr(), (dims[0] + 1) * sizeof(N),
+                            nullptr);
+  if (rc == SB200_OK)
+    rc = sb200_memcpy_d2d(dev, d_col, src_dev, csr->get_col(), nnz * sizeof(I), nullptr);
+  if constexpr (!std::is_void_v<V>) {
+    if (rc == SB200_OK && d_val)
+      rc = sb200_memcpy_d2d(dev, d_val, src_dev, csr->get_vals(), nnz * sizeof(V), nullptr);
+  }
+  sb200_stream_synchronize(dev, nullptr);
+  if (rc != SB200_OK) dev_free(dev, d_ptr), dev_free(dev, d_col), dev_free(dev, d_val);
+  check(rc, dev);
+  return new sbase::format::CUDACSR<I, N, V>(dims[0], dims[1], nnz, d_ptr, d_col, d_val, *ctx,
                                              sbase::format::kOwned);
 }
 
@@ -207,6 +369,31 @@ void RegisterConversions(sbase::converter::Converter &conv) {
                                     CUDACsrCsc<I, N, V>, CUDAToCPU, mv);
     conv.RegisterConversionFunction(CUDACSR<I, N, V>::get_id_static(), COO<I, N, V>::get_id_static(),
                                     CUDACsrCoo<I, N, V>, CUDAToCPU, mv);
+  }
+}
+
+inline bool CUDAToCUDA(sbase::context::Context *from, sbase::context::Context *to) {
+  return from->get_id() == sbase::context::CUDAContext::get_id_static() &&
+         to->get_id() == sbase::context::CUDAContext::get_id_static();
+}
+
+// Replaces SparseBase's own CSR <-> CUDACSR / CUDACSR -> CUDACSR functions in `conv` (a converter
+// takes the FIRST registered function whose condition holds, so the old ones are cleared).
+template <typename I, typename N, typename V>
+void RegisterTransfers(sbase::converter::Converter &conv) {
+  using namespace sbase::format;
+  for (bool mv : {false, true}) {
+    conv.ClearConversionFunctions(CSR<I, N, V>::get_id_static(), CUDACSR<I, N, V>::get_id_static(), mv);
+    conv.ClearConversionFunctions(CUDACSR<I, N, V>::get_id_static(), CSR<I, N, V>::get_id_static(), mv);
+    conv.ClearConversionFunctions(CUDACSR<I, N, V>::get_id_static(),
+                                  CUDACSR<I, N, V>::get_id_static(), mv);
+    conv.RegisterConversionFunction(CSR<I, N, V>::get_id_static(), CUDACSR<I, N, V>::get_id_static(),
+                                    CsrCUDACsr<I, N, V>, CPUToCUDA, mv);
+    conv.RegisterConversionFunction(CUDACSR<I, N, V>::get_id_static(), CSR<I, N, V>::get_id_static(),
+                                    CUDACsrCsr<I, N, V>, CUDAToCPU, mv);
+    conv.RegisterConversionFunction(CUDACSR<I, N, V>::get_id_static(),
+                                    CUDACSR<I, N, V>::get_id_static(), CUDACsrCUDACsr<I, N, V>,
+                                    CUDAToCUDA, mv);
   }
 }
 

@@ -197,13 +197,13 @@ def coo_to_csr(ops, n, m, bounds, row, col, vals, group=None, nnz_dtype=torch.in
 
 
 # ------------------------------------------------------------------------------- features
-def degrees(ops, s: ShardedCSR, id_dtype=torch.int32):
-    lo, hi = s.bounds[_world()[0]], s.bounds[_world()[0] + 1]
+def degrees(ops, s: ShardedCSR, id_dtype=torch.int32, group=None):
+    lo, hi = s.block(_world(group)[0])
     return ops.degrees(hi - lo, s.row_ptr, id_dtype=id_dtype)
 
 
-def degree_distribution(ops, s: ShardedCSR, feature_dtype=torch.float32):
-    rank, _ = _world()
+def degree_distribution(ops, s: ShardedCSR, feature_dtype=torch.float32, group=None):
+    rank, _ = _world(group)
     lo, hi = s.block(rank)
     return ops.degree_distribution(hi - lo, s.nnz, s.row_ptr, feature_dtype=feature_dtype)
 

@@ -19,3 +19,18 @@ def test_reference_dispatch_reaches_sb200_and_results_match():
     r = subprocess.run([DEMO], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "ALL EQUAL" in r.stdout
+
+
+@pytest.mark.gpu
+def test_plugin_end_to_end_host_csr_in_host_csr_out():
+    """oracle/plugin_bench.cc: RCMReorder + Permute2D through the reference's own API with a host
+    format::CSR in and host arrays out (the plugin's staged CSR <-> CUDACSR transfers), checked
+    against the reference's CPU functions in the same process."""
+    import json
+    exe = os.path.join(ROOT, "oracle", "_ref", "plugin_bench")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/plugin_bench not built (needs the reference tree: make -C oracle ref)")
+    r = subprocess.run([exe, "700", "1", "--check"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["parity"] is True and line["nnz"] == 5 * 700 * 700 - 4 * 700
