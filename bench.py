@@ -299,7 +299,22 @@ def rcm_block(lib, dev, peak, grid=4096, reps=3):
     same = np.array_equal(inv.cpu().numpy(), e_inv) and all(
         np.array_equal(a.cpu().numpy().view(np.uint8), b.view(np.uint8)) for a, b in zip(out, e_out))
     p2d_gbs = ALG_BYTES["permute2d"](n, nnz) / (p2d_ms * 1e-3) / 1e9
-    return {"workload": f"C2: RCMReorder + Permute2D on 2-D Poisson 5-point {grid}x{grid} "
+    # the same step as a SparseBase user gets it: host format::CSR in, host arrays out, through
+    # the UNMODIFIED reference's dispatch with the sb200 plugin registered (oracle/plugin_bench.cc)
+    e2e_plugin = None
+    exe = os.path.join(ROOT, "oracle", "_ref", "plugin_bench")
+    if os.path.exists(exe):
+        del out, rp, col, vals
+        torch.cuda.empty_cache()
+        lib.trim()
+        try:
+            r = subprocess.run([exe, str(grid), "3"], capture_output=True, text=True, timeout=600)
+            e2e_plugin = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else \
+                {"error": (r.stdout + r.stderr)[-300:]}
+        except Exception as exc:  # noqa: BLE001
+            e2e_plugin = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    return {"e2e_plugin": e2e_plugin,
+            "workload": f"C2: RCMReorder + Permute2D on 2-D Poisson 5-point {grid}x{grid} "
                         f"({n} rows, {nnz} nnz)",
             "rcm_ms": rcm_ms, "permute2d_ms": p2d_ms, "gnnz_per_s": nnz / ((rcm_ms + p2d_ms) * 1e-3) / 1e9,
             "permute2d_roofline_frac": p2d_gbs / peak,

@@ -1,0 +1,37 @@
+"""Permute2D with the DegreeReorder permutation on an R-MAT graph (the C4 shape): ms per call.
+    python profiles/p2d_time.py --scale 26 [--graph rmat|er]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sparsebase_b200 import lib, synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--scale", type=int, default=26)
+ap.add_argument("--graph", default="rmat")
+ap.add_argument("--reps", type=int, default=3)
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+lib.load()
+if args.graph == "rmat":
+    n, row, col = synth.rmat(args.scale, 8, seed=44, device=dev)
+else:
+    n, row, col = synth.erdos_renyi(1 << args.scale, 8, seed=43, device=dev)
+vals = synth.hash_vals(col.numel(), seed=7, device=dev)
+rp, cc, cv = lib.coo_to_csr(n, n, row, col, vals)
+del row, col, vals
+inv = lib.degree_reorder(n, rp, True)
+out = (torch.empty_like(rp), torch.empty_like(cc), torch.empty_like(cv))
+lib.permute2d(n, n, rp, cc, cv, inv, inv, out=out)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(args.reps):
+    lib.permute2d(n, n, rp, cc, cv, inv, inv, out=out)
+b.record()
+torch.cuda.synchronize()
+print(f"P2D_TIME graph={args.graph} scale={args.scale} nnz={cc.numel()} split={os.environ.get('SB200_P2D_SPLIT', 'auto')} "
+      f"ms={a.elapsed_time(b) / args.reps:.3f} checksum={int(out[1][::1000003].to(torch.int64).sum())}")

@@ -9,7 +9,10 @@
 // and writes it to its final place.  Every nonzero is read once and written once.
 //
 //   segment length <= 32   : rank-by-enumeration, one thread per entry
-//   33 .. kSsLong          : bitonic network run by one warp in shared memory
+//   33 .. kSsWarpMax       : bitonic network run by one warp in shared memory
+//   .. kSsLong             : the same network run by the whole CTA, one segment after the other
+//                            (one warp alone on a 1000-entry segment kept the other seven
+//                            waiting at the end of the CTA: 48 % of the kernel's stall samples)
 //   > kSsLong              : appended to a list; sorted afterwards by a segmented radix sort
 //                            on the index (radix_sort_segmented, see "long segments")
 //
@@ -30,6 +33,7 @@ constexpr int kSsTile = 1024;  // window of output positions per CTA
 constexpr int kSsLong = 1024;  // longest segment sorted on chip (must be >= kSsTile)
 constexpr int kSsCap = kSsTile + kSsLong;
 constexpr int kSsEnum = 32;
+constexpr int kSsWarpMax = 128;  // longest segment sorted by a single warp
 constexpr int kSsMaxMid = kSsCap / (kSsEnum + 1) + 1;
 constexpr int kSsScanPer = kSsCap / kSsBlock;  // consecutive positions per thread in the scan
 static_assert(kSsScanPer == 8, "the mark scan moves 8 u16 marks per thread as one 16-byte word");
@@ -235,10 +239,31 @@ __global__ void __launch_bounds__(kSsBlock)
     if constexpr (has_val<V>) st_stream(out_val + first + sb + rank, (V)s.val[q]);
   }
 
-  // ---- mid segments: one warp each, normalized bitonic network in shared memory ----
+  // ---- mid segments: normalized bitonic network in shared memory; comparator x of a step
+  //      works on (a2, b2), the low index a2 has bit j clear ----
   const unsigned nmid = s.nmid;
+  auto compare_exchange = [&](I *key, int sb, int len, int k, int j, int x) {
+    const bool flip = (j == (k >> 1));
+    const int a2 = ((x & ~(j - 1)) << 1) | (x & (j - 1));
+    const int b2 = flip ? (a2 ^ (k - 1)) : (a2 | j);
+    if (b2 < len) {
+      const I ka = key[a2], kb = key[b2];
+      if (kb < ka) {
+        key[a2] = kb;
+        key[b2] = ka;
+        if constexpr (has_val<V>) {
+          V *val = reinterpret_cast<V *>(s.val) + sb;
+          const V va = val[a2];
+          val[a2] = val[b2];
+          val[b2] = va;
+        }
+      }
+    }
+  };
+  // up to kSsWarpMax entries: one warp per segment
   for (unsigned mi = wid; mi < nmid; mi += kSsBlock / 32) {
     const int sb = (int)s.mid[mi], len = s.len[sb];
+    if (len > kSsWarpMax) continue;
     I *key = s.key + sb;
     for (int x = lane + 1; x < len; x += 32)
       if (key[x - 1] > key[x]) unsorted = true;
@@ -247,25 +272,7 @@ __global__ void __launch_bounds__(kSsBlock)
     while (P < len) P <<= 1;
     for (int k = 2; k <= P; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
-        const bool flip = (j == (k >> 1));
-        for (int x = lane; x < (P >> 1); x += 32) {
-          // x-th comparator of this step: low index a has bit j clear
-          const int a2 = ((x & ~(j - 1)) << 1) | (x & (j - 1));
-          const int b2 = flip ? (a2 ^ (k - 1)) : (a2 | j);
-          if (b2 < len) {
-            const I ka = key[a2], kb = key[b2];
-            if (kb < ka) {
-              key[a2] = kb;
-              key[b2] = ka;
-              if constexpr (has_val<V>) {
-                V *val = reinterpret_cast<V *>(s.val) + sb;
-                const V va = val[a2];
-                val[a2] = val[b2];
-                val[b2] = va;
-              }
-            }
-          }
-        }
+        for (int x = lane; x < (P >> 1); x += 32) compare_exchange(key, sb, len, k, j, x);
         __syncwarp();
       }
     }
@@ -276,6 +283,32 @@ __global__ void __launch_bounds__(kSsBlock)
       if constexpr (has_val<V>) st_stream(out_val + first + sb + x, reinterpret_cast<V *>(s.val)[sb + x]);
     }
     if (dc.seg_flag && __any_sync(0xffffffffu, dup) && lane == 0)
+      dc.flag(ss_segment_of<N>(ptr, n_seg, first + sb));
+  }
+  // longer ones: the whole CTA on one segment at a time (uniform control flow: the list and the
+  // lengths are in shared memory)
+  for (unsigned mi = 0; mi < nmid; mi++) {
+    const int sb = (int)s.mid[mi], len = s.len[sb];
+    if (len <= kSsWarpMax) continue;
+    I *key = s.key + sb;
+    for (int x = threadIdx.x + 1; x < len; x += kSsBlock)
+      if (key[x - 1] > key[x]) unsorted = true;
+    __syncthreads();
+    int P = 256;
+    while (P < len) P <<= 1;
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int x = threadIdx.x; x < (P >> 1); x += kSsBlock) compare_exchange(key, sb, len, k, j, x);
+        __syncthreads();
+      }
+    }
+    bool dup = false;
+    for (int x = threadIdx.x; x < len; x += kSsBlock) {
+      if (x + 1 < len && key[x] == key[x + 1]) dup = true;
+      st_stream(out_idx + first + sb + x, key[x]);
+      if constexpr (has_val<V>) st_stream(out_val + first + sb + x, reinterpret_cast<V *>(s.val)[sb + x]);
+    }
+    if (dc.seg_flag && __syncthreads_or(dup ? 1 : 0) && threadIdx.x == 0)
       dc.flag(ss_segment_of<N>(ptr, n_seg, first + sb));
   }
   dc.report_unsorted(unsorted);
