@@ -18,6 +18,7 @@
 //                            windows, every source stores its column slices into the owner's
 //                            window, the owner interleaves them (source order = row order)
 //   sb200_mg_permute1d       out[order[i]] = vals[i] stored straight into the owner's window
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -98,23 +99,48 @@ __global__ void mg_bcast_tail_kernel(MgPeers p, size_t region, const char *__res
   if (i < bytes)
     for (int r = 0; r < p.world; r++) (p.data(r) + region + at_bytes)[i] = src[i];
 }
-// (at_bytes must be 16-byte aligned relative to the region when bytes >= 16: callers slice
-// arrays of 4- or 8-byte elements at arbitrary element offsets, so unaligned slices take the
-// byte path)
+// Slices of 4- or 8-byte elements start at arbitrary element offsets, so source and destination
+// rarely share their 16-byte phase: the destination side is aligned (a short scalar head, then
+// 16-byte stores -- NVLink moves full 128-byte lines per warp), the source side is read as
+// 4-byte words.
+__global__ void __launch_bounds__(256)
+    mg_bcast_words_kernel(MgPeers p, size_t region, const unsigned *__restrict__ src,
+                          size_t at_bytes, size_t words) {
+  const size_t head = ((16 - (at_bytes & 15)) & 15) / 4;  // words before the first aligned store
+  const size_t h = head < words ? head : words;
+  const size_t quads = (words - h) / 4;
+  const size_t tail0 = h + quads * 4;
+  for (int r = blockIdx.y; r < p.world; r += gridDim.y) {
+    unsigned *dst = reinterpret_cast<unsigned *>(p.data(r) + region + at_bytes);
+    uint4 *dq = reinterpret_cast<uint4 *>(dst + h);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < quads;
+         i += (size_t)gridDim.x * blockDim.x) {
+      const unsigned *s4 = src + h + i * 4;
+      dq[i] = make_uint4(s4[0], s4[1], s4[2], s4[3]);
+    }
+    if (blockIdx.x == 0) {
+      if (threadIdx.x < h) dst[threadIdx.x] = src[threadIdx.x];
+      if (tail0 + threadIdx.x < words) dst[tail0 + threadIdx.x] = src[tail0 + threadIdx.x];
+    }
+  }
+}
 void mg_bcast_slice(sb200_mg_comm *c, cudaStream_t st, size_t region, const void *src,
                     size_t at_bytes, size_t bytes) {
   if (bytes == 0) return;
+  const int sms = device_info(c->device).sm_count;
+  dim3 grid((unsigned)(sms * 4 / c->peers.world > 0 ? sms * 4 / c->peers.world : 1),
+            (unsigned)c->peers.world);
   const bool aligned = (at_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0);
   if (aligned && bytes >= 16) {
-    const int sms = device_info(c->device).sm_count;
-    dim3 grid((unsigned)(sms * 2 / c->peers.world > 0 ? sms * 2 / c->peers.world : 1),
-              (unsigned)c->peers.world);
     SB_LAUNCH(mg_bcast_slice_kernel, grid, 256, 0, st, c->peers, region, (const uint4 *)src,
               at_bytes, bytes);
     const size_t done = bytes / 16 * 16;
     if (done < bytes)
       SB_LAUNCH(mg_bcast_tail_kernel, 1, 16, 0, st, c->peers, region, (const char *)src, at_bytes,
                 done, bytes);
+  } else if (at_bytes % 4 == 0 && bytes % 4 == 0 && reinterpret_cast<uintptr_t>(src) % 4 == 0) {
+    SB_LAUNCH(mg_bcast_words_kernel, grid, 256, 0, st, c->peers, region, (const unsigned *)src,
+              at_bytes, bytes / 4);
   } else {
     for (int r = 0; r < c->peers.world; r++)
       SB_CUDA(cudaMemcpyAsync(c->peers.data(r) + region + at_bytes, src, bytes,
@@ -137,7 +163,9 @@ static void check_barriers(const sb200_mg_comm *c) {
 class MgTrace {
  public:
   MgTrace(const sb200_mg_comm *c, cudaStream_t st, const char *op)
-      : on_(c->peers.rank == 0 && getenv("SB200_MG_TRACE") != nullptr), st_(st), op_(op) {
+      : on_(false), rank_(c->peers.rank), st_(st), op_(op) {
+    const char *e = getenv("SB200_MG_TRACE");  // "1": rank 0, "all": every rank
+    on_ = e != nullptr && (c->peers.rank == 0 || strcmp(e, "all") == 0);
     mark("start");
   }
   void mark(const char *name) {
@@ -151,7 +179,7 @@ class MgTrace {
   ~MgTrace() {
     if (!on_) return;
     cudaStreamSynchronize(st_);
-    std::string line = std::string("[mg-trace] ") + op_ + ":";
+    std::string line = std::string("[mg-trace] r") + std::to_string(rank_) + " " + op_ + ":";
     for (size_t i = 1; i < ev_.size(); i++) {
       float ms = 0;
       cudaEventElapsedTime(&ms, ev_[i - 1], ev_[i]);
@@ -165,6 +193,7 @@ class MgTrace {
 
  private:
   bool on_;
+  int rank_;
   cudaStream_t st_;
   const char *op_;
   std::vector<cudaEvent_t> ev_;
@@ -178,6 +207,35 @@ static void check_comm(const sb200_mg_comm *c) {
   for (int r = 0; r < c->peers.world; r++)
     SB_REQUIRE(c->peers.win[r] != nullptr, SB200_ERR_BAD_ARG,
                "communicator not connected (peer %d)", r);
+}
+
+// second stream (+ an event) of a communicator: exchanges that overlap local work
+constexpr int kMgMaxChunks = 16;
+static int mg_push_chunks() {
+  const char *e = getenv("SB200_MG_CHUNKS");
+  int k = e ? atoi(e) : 4;
+  return k < 1 ? 1 : (k > kMgMaxChunks ? kMgMaxChunks : k);
+}
+static int64_t mg_push_chunk_min() {  // entries below which a chunk is not worth its launches
+  const char *e = getenv("SB200_MG_CHUNK_MIN");
+  const long long v = e ? atoll(e) : (1ll << 20);
+  return v < 1 ? 1 : v;
+}
+static cudaStream_t mg_aux_stream(sb200_mg_comm *c) {
+  if (!c->aux_stream) {
+    cudaStream_t s;
+    SB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    c->aux_stream = s;
+  }
+  return (cudaStream_t)c->aux_stream;
+}
+static cudaEvent_t mg_aux_event(sb200_mg_comm *c) {
+  if (!c->aux_event) {
+    cudaEvent_t e;
+    SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->aux_event = e;
+  }
+  return (cudaEvent_t)c->aux_event;
 }
 
 // ------------------------------------------------------------------ Permute1D
@@ -236,6 +294,12 @@ __global__ void mg_new_degree_kernel(const N *__restrict__ deg, const I *__restr
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) new_deg[row_order ? (int64_t)row_order[i] : i] = deg[i];
 }
+template <typename N>
+__global__ void mg_rebase_ptr_kernel(const N *__restrict__ ptr, int64_t count, N base,
+                                     N *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = ptr[i] - base;
+}
 // bounds[k] = first new row whose new_ptr >= k * nnz / world (as sb200_partition_rows)
 template <typename N>
 __global__ void mg_balance_kernel(const N *__restrict__ ptr, int64_t n, int64_t nnz, int parts,
@@ -264,6 +328,9 @@ __global__ void mg_balance_kernel(const N *__restrict__ ptr, int64_t n, int64_t 
 }
 // The rows of this rank (already renumbered and sorted in `tcol` / `tval`, laid out by the
 // block-local row_ptr) go into the windows of the ranks that own their new row ids.
+// (Tried: local rows sorted by new id first, so that the remote stores become long runs -- the
+// push of the low-degree block of R-MAT-26 went from 12.0 to 5.8 ms at 4 GPUs, but the local
+// gather of the now scattered 2-entry rows cost 8 ms more than that.)
 // Balanced over ENTRIES, not rows (the heavy rows of a power-law matrix sit next to each other:
 // with one warp per 32 rows ncu showed 11 % of the warps active): every warp takes kMgPushChunk
 // consecutive entries, finds the row holding the first one by binary search, and walks the rows
@@ -516,6 +583,7 @@ int sb200_degrees(int, int64_t, const void *, void *, int, int, void *);
 int sb200_permute2d(int, int64_t, int64_t, int64_t, const void *, const void *, const void *,
                     const void *, const void *, void *, void *, void *, int, int, int, void *);
 int sb200_max_degree(int, int64_t, const void *, int, int64_t *, void *);
+int sb200_rank_keys(int, int64_t, const void *, int64_t, void *, int, void *);
 }
 
 #define SB_RC(expr)                                  \
@@ -619,6 +687,8 @@ int sb200_mg_comm_destroy(sb200_mg_comm_t *c) {
       if (c->ipc) cudaIpcCloseMemHandle(c->peers.win[r]);
     }
     if (c->owns_window && c->peers.win[c->peers.rank]) cudaFree(c->peers.win[c->peers.rank]);
+    if (c->aux_event) cudaEventDestroy((cudaEvent_t)c->aux_event);
+    if (c->aux_stream) cudaStreamDestroy((cudaStream_t)c->aux_stream);
     cudaGetLastError();
     delete c;
   });
@@ -761,9 +831,11 @@ int sb200_mg_degree_reorder(sb200_mg_comm_t *c, int64_t n, const int64_t *h_boun
     const int ib = dtype_size(id_type);
     SB_REQUIRE(ib == 4 || ib == 8, SB200_ERR_BAD_DTYPE, "bad id_type");
     Workspace ws(c->device, st);
+    MgTrace tr(c, st, "degree_reorder");
     // block-local order (degree ascending, id descending)
     void *local = ws.alloc_bytes((size_t)(nl > 0 ? nl : 1) * ib);
     SB_RC(sb200_degree_reorder(c->device, nl, row_ptr, 1, local, id_type, nnz_type, stream));
+    tr.mark("local_order");
     // largest degree anywhere
     int64_t my_max = 0;
     SB_RC(sb200_max_degree(c->device, nl, row_ptr, nnz_type, &my_max, stream));
@@ -772,6 +844,7 @@ int sb200_mg_degree_reorder(sb200_mg_comm_t *c, int64_t n, const int64_t *h_boun
     int64_t maxdeg = 0;
     for (int r = 0; r < world; r++) maxdeg = std::max(maxdeg, all[r]);
     const int64_t nbins = maxdeg + 1;
+    tr.mark("max_degree_allgather");
     MgLayout lay(c);
     const size_t hist_region = lay.take((size_t)world * nbins * sizeof(unsigned long long));
     const size_t inv_region = lay.take((size_t)n * ib);
@@ -781,6 +854,7 @@ int sb200_mg_degree_reorder(sb200_mg_comm_t *c, int64_t n, const int64_t *h_boun
     mg_bcast_slice(c, st, hist_region, hist, (size_t)rank * nbins * sizeof(unsigned long long),
                    (size_t)nbins * sizeof(unsigned long long));
     mg_barrier(c, st);
+    tr.mark("histogram_allgather");
     const unsigned long long *all_hist =
         reinterpret_cast<const unsigned long long *>(c->peers.data(rank) + hist_region);
     int64_t *g_start = ws.alloc<int64_t>(nbins + 1), *l_start = ws.alloc<int64_t>(nbins + 1);
@@ -792,11 +866,15 @@ int sb200_mg_degree_reorder(sb200_mg_comm_t *c, int64_t n, const int64_t *h_boun
     void *part = ws.alloc_bytes((size_t)(nl > 0 ? nl : 1) * ib);
     SB_RC(sb200_degree_rank_combine(c->device, nl, row_ptr, local, offset,
                                     ascending ? -1 : n - 1, part, id_type, nnz_type, stream));
+    tr.mark("offsets_and_rank");
     mg_bcast_slice(c, st, inv_region, part, (size_t)lo * ib, (size_t)nl * ib);
+    tr.mark("bcast_slice");
     mg_barrier(c, st);
+    tr.mark("barrier");
     SB_CUDA(cudaMemcpyAsync(out_inv, c->peers.data(rank) + inv_region, (size_t)n * ib,
                             cudaMemcpyDeviceToDevice, st));
     mg_barrier(c, st);
+    tr.mark("copy_out");
   });
 }
 
@@ -870,23 +948,68 @@ int sb200_mg_permute2d_run(sb200_mg_comm_t *c, int64_t n, int64_t m, int64_t nnz
       SB_REQUIRE((size_t)new_nnz <= room, SB200_ERR_BAD_ARG,
                  "multi-GPU window too small for the permuted block (%lld entries, room for %zu)",
                  (long long)new_nnz, room);
-      N *t_ptr = ws.alloc<N>(nl + 1);
+      // ---- my rows: renumber the columns and sort every row (rows stay in their old order),
+      // then every row goes to its final place in the owner's window.  The block is cut into
+      // chunks of rows with about the same number of entries: while the SMs sort chunk k + 1,
+      // the stores of chunk k are on the wire (second stream) -- the push of a block of 2-entry
+      // rows is bound by the small NVLink writes, not by anything the sort needs.
+      N *t_ptr = ws.alloc<N>(nl + 1 + kMgMaxChunks);
       I *t_col = ws.alloc<I>(my_nnz > 0 ? my_nnz : 1);
       V *t_val = nullptr;
       if constexpr (has_val<V>) t_val = ws.alloc<V>(my_nnz > 0 ? my_nnz : 1);
-      SB_RC(sb200_permute2d(c->device, nl, m, my_nnz, row_ptr, col, hv ? vals : nullptr, nullptr,
-                            col_order, t_ptr, t_col, t_val, id_type, nnz_type,
-                            hv ? val_type : SB200_VOID, stream));
+      int chunks = mg_push_chunks();
+      if (world == 1 || my_nnz < (int64_t)chunks * mg_push_chunk_min()) chunks = 1;
+      std::vector<int64_t> cb(chunks + 1, 0), cat(chunks + 1, 0);
+      cb[chunks] = nl;
+      cat[chunks] = my_nnz;
+      if (chunks > 1) {
+        int64_t *d_cb = ws.alloc<int64_t>(chunks + 1), *d_cat = ws.alloc<int64_t>(chunks + 1);
+        SB_LAUNCH((mg_balance_kernel<N>), 1, 32, 0, st, (const N *)row_ptr, nl, my_nnz, chunks,
+                  d_cb, d_cat);
+        SB_CUDA(cudaMemcpyAsync(cb.data(), d_cb, (chunks + 1) * sizeof(int64_t),
+                                cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaMemcpyAsync(cat.data(), d_cat, (chunks + 1) * sizeof(int64_t),
+                                cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+      }
+      cudaStream_t push_st = chunks > 1 ? mg_aux_stream(c) : st;
+      cudaEvent_t ev = mg_aux_event(c);
+      const int sms = device_info(c->device).sm_count;
+      N *sub_ptr = t_ptr;
+      for (int k = 0; k < chunks; k++) {
+        const int64_t r0 = cb[k], rows = cb[k + 1] - cb[k];
+        const int64_t e0 = cat[k], ents = cat[k + 1] - cat[k];
+        if (rows <= 0) continue;
+        // (the chunk as a CSR of its own: row_ptr rebased to the chunk's first entry)
+        N *in_ptr = ws.alloc<N>(rows + 1);
+        SB_LAUNCH((mg_rebase_ptr_kernel<N>), (unsigned)ceil_div(rows + 1, 256), 256, 0, st,
+                  (const N *)row_ptr + r0, rows + 1, (N)e0, in_ptr);
+        SB_RC(sb200_permute2d(c->device, rows, m, ents, in_ptr, (const I *)col + e0,
+                              hv ? (const void *)((const V *)vals + e0) : nullptr, nullptr,
+                              col_order, sub_ptr, t_col + e0, hv ? (void *)(t_val + e0) : nullptr,
+                              id_type, nnz_type, hv ? val_type : SB200_VOID, stream));
+        if (ents > 0) {
+          if (push_st != st) {
+            SB_CUDA(cudaEventRecord(ev, st));
+            SB_CUDA(cudaStreamWaitEvent(push_st, ev, 0));
+          }
+          // (overlapped with the next chunk's sort: a push that filled every SM with warps
+          // waiting on NVLink kept the sort kernels out -- two CTAs per SM are enough to keep
+          // the links busy)
+          const int64_t warps = std::min<int64_t>(ceil_div(ents, kMgPushChunk),
+                                                  (int64_t)sms * (push_st != st ? 16 : 64));
+          SB_LAUNCH((mg_push_rows_kernel<I, N, V>), (unsigned)ceil_div(warps * 32, 256), 256, 0,
+                    push_st, c->peers, col_region, val_region, (const N *)sub_ptr,
+                    (const I *)(t_col + e0), (const V *)(hv ? t_val + e0 : nullptr),
+                    (const I *)row_order, lo + r0, rows, ents, (const N *)new_ptr,
+                    (const int64_t *)nb, (const int64_t *)nb_at);
+        }
+        sub_ptr += rows + 1;
+      }
       tr.mark("local_renumber_sort");
-      // ---- every row goes to its final place in the owner's window
-      if (nl > 0 && my_nnz > 0) {
-        const int sms = device_info(c->device).sm_count;
-        const int64_t warps =
-            std::min<int64_t>(ceil_div(my_nnz, kMgPushChunk), (int64_t)sms * 64);
-        SB_LAUNCH((mg_push_rows_kernel<I, N, V>), (unsigned)ceil_div(warps * 32, 256), 256, 0, st,
-                  c->peers, col_region, val_region, (const N *)t_ptr, (const I *)t_col,
-                  (const V *)t_val, (const I *)row_order, lo, nl, my_nnz, (const N *)new_ptr,
-                  (const int64_t *)nb, (const int64_t *)nb_at);
+      if (push_st != st) {
+        SB_CUDA(cudaEventRecord(ev, push_st));
+        SB_CUDA(cudaStreamWaitEvent(st, ev, 0));
       }
       tr.mark("push_rows");
       mg_barrier(c, st);

@@ -43,6 +43,8 @@ struct sb200_mg_comm {
   unsigned long long epoch; // barriers issued so far (same on every rank)
   bool ipc;                 // peers opened through CUDA IPC (to be closed)
   bool owns_window;
+  void *aux_stream = nullptr;  // cudaStream_t, created on first use (overlapped exchanges)
+  void *aux_event = nullptr;   // cudaEvent_t
 };
 
 namespace sb200 {

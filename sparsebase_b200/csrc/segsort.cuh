@@ -488,6 +488,225 @@ __global__ void __launch_bounds__(256)
   if (dc.seg_flag && __syncthreads_or(dup ? 1 : 0) && threadIdx.x == 0) dc.flag(list[k]);
 }
 
+// ------------------------------------------------------------------ big segments
+// Segments longer than kSsLong that still fit in shared memory are sorted by ONE CTA entirely
+// on chip: gather + renumber into shared memory, ceil(bits / 9) stable LSD passes between two
+// shared buffers (every warp owns a contiguous part of the segment: per-warp digit counts, one
+// scan over (digit, warp), ranks inside a batch of 32 from nine ballots -- no atomics: ATOMS
+// costs 2 cycles per lane, MATCH.ANY one step per distinct digit), one coalesced write.  The
+// segmented global radix sort below moves these entries through HBM once per pass in runs of a
+// few entries per digit (a 2 000-entry segment has 8 entries per digit): 21 of the 54 ms of
+// Permute2D on R-MAT-26.  Two shapes: 256 threads / 72 KB (three CTAs per SM: one gathers
+// while the others sort) for segments up to 3 072 entries (4-byte ids and values), 512 threads
+// / 200 KB up to 9 216.  A segment that does not fit is appended to `next_list`.
+constexpr int kSbDigitBits = 9;
+constexpr int kSbBins = 1 << kSbDigitBits;
+template <int THREADS>
+constexpr int ss_big_hist_bytes() {
+  return (THREADS / 32) * kSbBins * (int)sizeof(unsigned);
+}
+template <typename I, typename V>
+constexpr int ss_big_entry_bytes() {  // two (key, value) buffers + the 2-byte rank of the pass
+  return 2 * ((int)sizeof(I) + (has_val<V> ? (int)sizeof(V) : 0)) + 2;
+}
+template <typename I, typename V, int THREADS, int BUDGET_KB>
+constexpr int ss_big_cap() {
+  return ((BUDGET_KB * 1024 - ss_big_hist_bytes<THREADS>()) / ss_big_entry_bytes<I, V>()) / 512 *
+         512;
+}
+template <typename I, typename V, int THREADS, int BUDGET_KB>
+constexpr int ss_big_smem() {
+  return ss_big_cap<I, V, THREADS, BUDGET_KB>() * ss_big_entry_bytes<I, V>() +
+         ss_big_hist_bytes<THREADS>();
+}
+
+// lanes with the same digit, for two independent batches at once (the two chains of dependent
+// VOTE results interleave)
+__device__ __forceinline__ void sb_match_digit2(unsigned da, unsigned db, int bits,
+                                                unsigned &peers_a, unsigned &peers_b) {
+  unsigned pa = 0xffffffffu, pb = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < kSbDigitBits; b++) {
+    if (b < bits) {  // (warp-uniform)
+      const bool bit_a = (da & (1u << b)) != 0u, bit_b = (db & (1u << b)) != 0u;
+      const unsigned bal_a = __ballot_sync(0xffffffffu, bit_a);
+      const unsigned bal_b = __ballot_sync(0xffffffffu, bit_b);
+      pa &= bit_a ? bal_a : ~bal_a;
+      pb &= bit_b ? bal_b : ~bal_b;
+    }
+  }
+  peers_a = pa;
+  peers_b = pb;
+}
+
+// grid: one CTA per entry of `list` (n_list read on the device when list_count is given: the
+// second shape is launched before the host knows how many segments the first one passed on).
+template <typename I, typename N, typename V, typename Loader, int THREADS, int BUDGET_KB>
+__global__ void __launch_bounds__(THREADS)
+    ss_big_kernel(Loader ld, const N *__restrict__ ptr, const int64_t *__restrict__ list,
+                  const unsigned *__restrict__ list_count, int idx_bits, I *__restrict__ out_idx,
+                  V *__restrict__ out_val, int64_t *__restrict__ next_list,
+                  unsigned *__restrict__ next_count, DupCtx dc) {
+  using UI = typename std::make_unsigned<I>::type;
+  constexpr int CAP = ss_big_cap<I, V, THREADS, BUDGET_KB>();
+  constexpr int WARPS = THREADS / 32;
+  extern __shared__ __align__(16) unsigned char sb_raw[];
+  __shared__ unsigned digit_base[kSbBins];
+  __shared__ unsigned warp_tot[kSbBins / 32];
+  if (list_count && blockIdx.x >= *list_count) return;
+  UI *k0 = reinterpret_cast<UI *>(sb_raw), *k1 = k0 + CAP;
+  V *v0 = nullptr, *v1 = nullptr;
+  unsigned *hist;
+  if constexpr (has_val<V>) {
+    v0 = reinterpret_cast<V *>(k1 + CAP);
+    v1 = v0 + CAP;
+    hist = reinterpret_cast<unsigned *>(v1 + CAP);
+  } else {
+    hist = reinterpret_cast<unsigned *>(k1 + CAP);
+  }
+  // loc[q] = rank of entry q among the entries of its digit inside its warp's part
+  unsigned short *loc = reinterpret_cast<unsigned short *>(hist + WARPS * kSbBins);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int64_t seg = list[blockIdx.x];
+  const int64_t dst0 = (int64_t)ptr[seg];
+  const int64_t len64 = (int64_t)ptr[seg + 1] - dst0;
+  if (len64 > CAP) {
+    if (tid == 0) next_list[atomicAdd(next_count, 1u)] = seg;
+    return;
+  }
+  const int len = (int)len64;
+  const int64_t src0 = ld.seg_base(seg);
+  // ---- gather (coalesced inside the source row, renumbering gathers batched)
+  constexpr int kBatch = 4;
+  for (int q0 = 0; q0 < len; q0 += THREADS * kBatch) {
+    I raw[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int q = q0 + u * THREADS + tid;
+      if (q < len) {
+        raw[u] = ld.raw_key(src0 + q);
+        if constexpr (has_val<V>) v0[q] = ld.val(src0 + q);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int q = q0 + u * THREADS + tid;
+      if (q < len) k0[q] = (UI)ld.map_key(raw[u]);
+    }
+  }
+  __syncthreads();
+  bool unsorted = false;
+  if (dc.unsorted)
+    for (int q = tid + 1; q < len; q += THREADS)
+      if (k0[q - 1] > k0[q]) unsorted = true;
+  dc.report_unsorted(unsorted);
+  // ---- LSD passes
+  const int P = (idx_bits + kSbDigitBits - 1) / kSbDigitBits;
+  const int per_warp = (((len + WARPS - 1) / WARPS) + 31) & ~31;
+  const int wb = w * per_warp < len ? w * per_warp : len;
+  const int we = wb + per_warp < len ? wb + per_warp : len;
+  unsigned *my_hist = hist + w * kSbBins;
+  int shift = 0;
+  for (int pass = 0; pass < P; pass++) {
+    const int bits = (idx_bits - shift + (P - pass) - 1) / (P - pass);
+    const int nbins = 1 << bits;
+    const unsigned mask = (unsigned)nbins - 1u;
+    for (int k = tid; k < WARPS * kSbBins; k += THREADS) hist[k] = 0;
+    __syncthreads();
+    // digit counts of my part + every entry's rank inside its digit (two batches of 32 per
+    // step; the lowest lane of a group of equal digits moves the counter)
+    for (int base = wb; base < we; base += 64) {
+      const int qa = base + lane, qb = qa + 32;
+      const bool in_a = qa < we, in_b = qb < we;
+      const unsigned da = in_a ? ((unsigned)(k0[qa] >> shift) & mask) : mask;
+      const unsigned db = in_b ? ((unsigned)(k0[qb] >> shift) & mask) : mask;
+      unsigned pa, pb;
+      sb_match_digit2(da, db, bits, pa, pb);
+      pa &= __ballot_sync(0xffffffffu, in_a);
+      pb &= __ballot_sync(0xffffffffu, in_b);
+      const unsigned lt = (1u << lane) - 1u;
+      const int lead_a = __ffs(pa) - 1, lead_b = __ffs(pb) - 1;
+      unsigned cur = 0;
+      if (in_a && lane == lead_a) {
+        cur = my_hist[da];
+        my_hist[da] = cur + __popc(pa);
+      }
+      cur = __shfl_sync(0xffffffffu, cur, lead_a & 31);
+      if (in_a) loc[qa] = (unsigned short)(cur + __popc(pa & lt));
+      __syncwarp();
+      cur = 0;
+      if (in_b && lane == lead_b) {
+        cur = my_hist[db];
+        my_hist[db] = cur + __popc(pb);
+      }
+      cur = __shfl_sync(0xffffffffu, cur, lead_b & 31);
+      if (in_b) loc[qb] = (unsigned short)(cur + __popc(pb & lt));
+      __syncwarp();
+    }
+    __syncthreads();
+    // hist[w][d] -> entries of digit d in the warps before w; digit_base[d] -> smaller digits
+    for (int d0 = 0; d0 < nbins; d0 += THREADS) {  // (block-uniform trip count)
+      const int d = d0 + tid;
+      unsigned tot = 0;
+      if (d < nbins) {
+#pragma unroll
+        for (int ww = 0; ww < WARPS; ww++) {
+          const unsigned c = hist[ww * kSbBins + d];
+          hist[ww * kSbBins + d] = tot;
+          tot += c;
+        }
+      }
+      const unsigned incl = warp_inclusive_scan(tot);
+      if (lane == 31) warp_tot[(d0 >> 5) + w] = incl;
+      if (d < nbins) digit_base[d] = incl - tot;  // exclusive inside its group of 32 digits
+    }
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of the (at most 16) group totals
+      const int groups = (nbins + 31) >> 5;
+      const unsigned t = tid < groups ? warp_tot[tid] : 0u;
+      const unsigned incl = warp_inclusive_scan(t);
+      if (tid < groups) warp_tot[tid] = incl - t;
+    }
+    __syncthreads();
+    // (no ranking left to do: position = smaller digits + same digit in the warps before
+    // mine + rank inside my part)
+    for (int q = wb + lane; q < we; q += 32) {
+      const UI key = k0[q];
+      const unsigned d = (unsigned)(key >> shift) & mask;
+      const unsigned pos = digit_base[d] + warp_tot[d >> 5] + my_hist[d] + loc[q];
+      k1[pos] = key;
+      if constexpr (has_val<V>) v1[pos] = v0[q];
+    }
+    __syncthreads();
+    UI *tk = k0;
+    k0 = k1;
+    k1 = tk;
+    if constexpr (has_val<V>) {
+      V *tv = v0;
+      v0 = v1;
+      v1 = tv;
+    }
+    shift += bits;
+  }
+  // ---- store
+  bool dup = false;
+  for (int q = tid; q < len; q += THREADS) {
+    const UI key = k0[q];
+    if (dc.seg_flag && q > 0 && k0[q - 1] == key) dup = true;
+    st_stream(out_idx + dst0 + q, (I)key);
+    if constexpr (has_val<V>) st_stream(out_val + dst0 + q, v0[q]);
+  }
+  if (dc.seg_flag && __syncthreads_or(dup ? 1 : 0) && tid == 0) dc.flag(seg);
+}
+
+inline bool ss_big_enabled() {  // SB200_SS_BIG=0: every long segment takes the global path
+  static const bool on = [] {
+    const char *e = getenv("SB200_SS_BIG");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 // Scratch of the duplicate-id rule for n_seg segments (flags zeroed on the stream).
 // `detect_unsorted` = false when the caller already knows that the sort happens.
 inline DupCtx make_dup_ctx(Workspace &ws, int64_t n_seg, bool detect_unsorted) {
@@ -545,8 +764,36 @@ void segmented_sort(Workspace &ws, Loader ld, const N *ptr, int64_t n_seg, int64
     return;
   }
 
-  // ---- long segments: segmented radix sort on the index ----
   using UI = typename std::make_unsigned<I>::type;
+  const int idx_bits = bits_for((uint64_t)(n_idx > 0 ? n_idx - 1 : 0));
+  // ---- big segments: one CTA each, on chip; what does not fit is listed for the global path
+  if (ss_big_enabled()) {
+    int64_t *mid_list = ws.alloc<int64_t>((int64_t)nlong);
+    int64_t *huge_list = ws.alloc<int64_t>((int64_t)nlong);
+    unsigned *counts = ws.alloc<unsigned>(2);
+    SB_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned), st));
+    auto k_small = ss_big_kernel<I, N, V, Loader, 256, 72>;
+    auto k_large = ss_big_kernel<I, N, V, Loader, 512, 200>;
+    constexpr int smem_small = ss_big_smem<I, V, 256, 72>();
+    constexpr int smem_large = ss_big_smem<I, V, 512, 200>();
+    SB_CUDA(cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 smem_small));
+    SB_CUDA(cudaFuncSetAttribute(k_large, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 smem_large));
+    SB_LAUNCH(k_small, nlong, 256, smem_small, st, ld, ptr, (const int64_t *)long_list,
+              (const unsigned *)nullptr, idx_bits, out_idx, out_val, mid_list, counts, dc);
+    SB_LAUNCH(k_large, nlong, 512, smem_large, st, ld, ptr, (const int64_t *)mid_list,
+              (const unsigned *)counts, idx_bits, out_idx, out_val, huge_list, counts + 1, dc);
+    SB_CUDA(cudaMemcpyAsync(&nlong, counts + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    if (nlong == 0) {
+      launch_dup_fix<I, N, V, Loader>(ws, ld, ptr, n_seg, dc, sort_known, out_idx, out_val, vkind);
+      return;
+    }
+    long_list = huge_list;
+  }
+
+  // ---- long segments: segmented radix sort on the index ----
   constexpr int kTileL = rs_seg_tile<UI, V, NoVal>();
   int64_t *offs = ws.alloc<int64_t>((int64_t)nlong + 1);
   int64_t *chunk_first = ws.alloc<int64_t>((int64_t)nlong + 1);
@@ -559,7 +806,6 @@ void segmented_sort(Workspace &ws, Loader ld, const N *ptr, int64_t n_seg, int64
                           st));
   SB_CUDA(cudaStreamSynchronize(st));
   SB_REQUIRE(nchunks < (1ll << 31), SB200_ERR_BAD_ARG, "too many long-segment chunks");
-  const int idx_bits = bits_for((uint64_t)(n_idx > 0 ? n_idx - 1 : 0));
   const int P = (idx_bits + kRsMaxBits - 1) / kRsMaxBits;
   RsSeg *seg = ws.alloc<RsSeg>(nchunks);
   int *chunk_seg = ws.alloc<int>(nchunks);

@@ -217,7 +217,11 @@ def test_long_rows_segmented_sort(sb, orc, types):
     idt, nt, vt = types
     rng = np.random.default_rng(41)
     n = 30011
-    lens = {0: 20000, 5: 9000, 6: 8192, 7: 8193, 11: 1025, 12: 1024, 29999: 16385}
+    # (3072 | 9216, 1536 | 4608, 5632 | 16896 = what one CTA of the two on-chip shapes sorts in
+    # shared memory for the three type sets)
+    lens = {0: 20000, 5: 9000, 6: 8192, 7: 8193, 11: 1025, 12: 1024, 29999: 16385, 40: 3072,
+            41: 3073, 42: 9216, 43: 9217, 44: 1536, 45: 1537, 46: 4608, 47: 4609, 48: 5632,
+            49: 5633, 50: 16896, 51: 16897, 52: 2047, 53: 3001}
     rows = [np.full(c, r) for r, c in lens.items()] + [rng.integers(13, n - 20, 50000)]
     cols = [rng.choice(n, c, replace=False) for c in lens.values()] + [rng.integers(0, n, 50000)]
     key = np.unique(np.concatenate(rows).astype(np.int64) * n + np.concatenate(cols))

@@ -92,8 +92,8 @@ def test_sharded_operators_nccl(graph, scale):
     assert r.returncode == 0 and "SHARDED OK" in r.stdout, r.stdout[-3000:] + r.stderr[-5000:]
 
 
-@pytest.mark.parametrize("graph,scale", [("rmat", 15), ("er", 16)])
-def test_peer_memory_operators(graph, scale):
+@pytest.mark.parametrize("graph,scale,chunks", [("rmat", 15, 0), ("er", 16, 0), ("rmat", 14, 5)])
+def test_peer_memory_operators(graph, scale, chunks):
     """The sb200_mg_* operators (peer-memory windows, CUDA IPC between the ranks) bit-equal to the
     single-GPU operators: tests/mg_gpu_worker.py under torchrun."""
     ngpu = torch.cuda.device_count()
@@ -104,7 +104,10 @@ def test_peer_memory_operators(graph, scale):
            "--master-addr", "127.0.0.1", "--master-port", "29541",
            os.path.join(ROOT, "tests", "mg_gpu_worker.py"), "--graph", graph, "--scale",
            str(scale)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    env = dict(os.environ)
+    if chunks:  # force the chunk-pipelined row push of Permute2D on a small graph
+        env.update(SB200_MG_CHUNKS=str(chunks), SB200_MG_CHUNK_MIN="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and "MG OK" in r.stdout, r.stdout[-3000:] + r.stderr[-5000:]
 
 
