@@ -18,6 +18,7 @@
 //                            windows, every source stores its column slices into the owner's
 //                            window, the owner interleaves them (source order = row order)
 //   sb200_mg_permute1d       out[order[i]] = vals[i] stored straight into the owner's window
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -166,6 +167,7 @@ class MgTrace {
       : on_(false), rank_(c->peers.rank), st_(st), op_(op) {
     const char *e = getenv("SB200_MG_TRACE");  // "1": rank 0, "all": every rank
     on_ = e != nullptr && (c->peers.rank == 0 || strcmp(e, "all") == 0);
+    t0_ = std::chrono::steady_clock::now();
     mark("start");
   }
   void mark(const char *name) {
@@ -187,6 +189,11 @@ class MgTrace {
       snprintf(buf, sizeof(buf), "  %s=%.3f", names_[i], ms);
       line += buf;
     }
+    char wall[64];
+    snprintf(wall, sizeof(wall), "  host_wall=%.3f",
+             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0_)
+                 .count());
+    line += wall;
     fprintf(stderr, "%s\n", line.c_str());
     for (cudaEvent_t e : ev_) cudaEventDestroy(e);
   }
@@ -194,6 +201,7 @@ class MgTrace {
  private:
   bool on_;
   int rank_;
+  std::chrono::steady_clock::time_point t0_;
   cudaStream_t st_;
   const char *op_;
   std::vector<cudaEvent_t> ev_;
@@ -213,8 +221,12 @@ static void check_comm(const sb200_mg_comm *c) {
 constexpr int kMgMaxChunks = 16;
 static int mg_push_chunks() {
   const char *e = getenv("SB200_MG_CHUNKS");
-  int k = e ? atoi(e) : 4;
+  int k = e ? atoi(e) : 1;
   return k < 1 ? 1 : (k > kMgMaxChunks ? kMgMaxChunks : k);
+}
+static bool mg_push_dest_order() {  // SB200_MG_PUSH_ORDER=source: rows pushed as they lie
+  const char *e = getenv("SB200_MG_PUSH_ORDER");
+  return !(e && e[0] == 's');
 }
 static int64_t mg_push_chunk_min() {  // entries below which a chunk is not worth its launches
   const char *e = getenv("SB200_MG_CHUNK_MIN");
@@ -294,6 +306,24 @@ __global__ void mg_new_degree_kernel(const N *__restrict__ deg, const I *__restr
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) new_deg[row_order ? (int64_t)row_order[i] : i] = deg[i];
 }
+template <typename I, typename UI>
+__global__ void mg_order_keys_kernel(const I *__restrict__ new_id, int64_t n_local,
+                                     UI *__restrict__ keys, UI *__restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_local) {
+    keys[i] = (UI)new_id[i];
+    idx[i] = (UI)i;
+  }
+}
+template <typename I, typename N>
+struct MgWalkLenFn {  // length of the k-th row of the walk
+  const N *ptr;
+  const I *sidx;
+  __device__ N operator()(int64_t k) const {
+    const int64_t i = (int64_t)sidx[k];
+    return ptr[i + 1] - ptr[i];
+  }
+};
 template <typename N>
 __global__ void mg_rebase_ptr_kernel(const N *__restrict__ ptr, int64_t count, N base,
                                      N *__restrict__ out) {
@@ -344,7 +374,12 @@ __global__ void __launch_bounds__(256)
                         const N *__restrict__ row_ptr, const I *__restrict__ tcol,
                         const V *__restrict__ tval, const I *__restrict__ row_order, int64_t row_lo,
                         int64_t n_local, int64_t nnz_local, const N *__restrict__ new_ptr,
-                        const int64_t *__restrict__ nb, const int64_t *__restrict__ nb_at) {
+                        const int64_t *__restrict__ nb, const int64_t *__restrict__ nb_at,
+                        const I *__restrict__ sidx, const I *__restrict__ dest_id,
+                        const N *__restrict__ dptr) {
+  // walk order: the local rows as they lie (sidx == null), or sorted by new id: the k-th row of
+  // the walk is local row sidx[k], its new id dest_id[k], and dptr is the row_ptr of that order
+  const N *__restrict__ walk = sidx ? dptr : row_ptr;
   const unsigned lane = lane_id();
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -355,33 +390,72 @@ __global__ void __launch_bounds__(256)
     int64_t lo = 0, hi = n_local;  // last row with row_ptr[row] <= e0
     while (hi - lo > 1) {
       const int64_t mid = (lo + hi) >> 1;
-      if ((int64_t)row_ptr[mid] <= e0)
+      if ((int64_t)walk[mid] <= e0)
         lo = mid;
       else
         hi = mid;
     }
     for (int64_t g = lo; g < n_local; g += 32) {
       const int64_t i = g + lane;
-      int64_t b = 0;
+      int64_t b = 0;  // first entry of the row inside the chunk, as a position in tcol / tval
       unsigned d = 0;
       I *oc = nullptr;
       V *ov = nullptr;
       int64_t row_begin = nnz_local;  // (rows past the end start beyond every chunk)
       if (i < n_local) {
-        row_begin = (int64_t)row_ptr[i];
-        const int64_t row_end = (int64_t)row_ptr[i + 1];
+        row_begin = (int64_t)walk[i];
+        const int64_t row_end = (int64_t)walk[i + 1];
         b = row_begin > e0 ? row_begin : e0;
         const int64_t e = row_end < e1 ? row_end : e1;
         if (e > b) {
           // destination: the owner of the new row id, at the row's final offset in its block
-          const int64_t j = row_order ? (int64_t)row_order[row_lo + i] : row_lo + i;
+          const int64_t j = sidx ? (int64_t)dest_id[i]
+                                 : (row_order ? (int64_t)row_order[row_lo + i] : row_lo + i);
           int r = 0;
           while (r + 1 < p.world && j >= nb[r + 1]) r++;
           const int64_t dst = (int64_t)new_ptr[j] - nb_at[r] + (b - row_begin);
           oc = reinterpret_cast<I *>(p.data(r) + col_region) + dst;
           if constexpr (has_val<V>) ov = reinterpret_cast<V *>(p.data(r) + val_region) + dst;
           d = (unsigned)(e - b);
+          if (sidx) b += (int64_t)row_ptr[sidx[i]] - row_begin;  // where the row lies locally
         }
+      }
+      // long runs first: the whole warp copies them with four independent loads per lane in
+      // flight (a hub row spans many chunks; its pieces are 4096-entry runs)
+      unsigned longs = __ballot_sync(0xffffffffu, d >= 128u);
+      while (longs) {
+        const int src = __ffs(longs) - 1;
+        longs &= longs - 1;
+        const unsigned len = __shfl_sync(0xffffffffu, d, src);
+        const int64_t from = __shfl_sync(0xffffffffu, b, src);
+        I *dc = reinterpret_cast<I *>(__shfl_sync(0xffffffffu, (unsigned long long)oc, src));
+        [[maybe_unused]] V *dv =
+            reinterpret_cast<V *>(__shfl_sync(0xffffffffu, (unsigned long long)ov, src));
+        for (unsigned k0 = 0; k0 < len; k0 += 128) {
+          I cbuf[4];
+          [[maybe_unused]] V vbuf[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const unsigned k = k0 + u * 32 + lane;
+            if (k < len) {
+              cbuf[u] = ld_stream(tcol + from + k);
+              if constexpr (has_val<V>) {
+                if (tval) vbuf[u] = ld_stream(tval + from + k);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const unsigned k = k0 + u * 32 + lane;
+            if (k < len) {
+              dc[k] = cbuf[u];
+              if constexpr (has_val<V>) {
+                if (tval) dv[k] = vbuf[u];
+              }
+            }
+          }
+        }
+        if ((int)lane == src) d = 0;
       }
       const unsigned incl = warp_inclusive_scan(d);
       const unsigned excl = incl - d;
@@ -408,7 +482,7 @@ __global__ void __launch_bounds__(256)
         }
       }
       // the next 32 rows start at or beyond the end of the chunk: done
-      if (__shfl_sync(0xffffffffu, i + 1 < n_local ? (int64_t)row_ptr[i + 1] : nnz_local, 31) >= e1)
+      if (__shfl_sync(0xffffffffu, i + 1 < n_local ? (int64_t)walk[i + 1] : nnz_local, 31) >= e1)
         break;
     }
   }
@@ -993,20 +1067,43 @@ int sb200_mg_permute2d_run(sb200_mg_comm_t *c, int64_t n, int64_t m, int64_t nnz
             SB_CUDA(cudaEventRecord(ev, st));
             SB_CUDA(cudaStreamWaitEvent(push_st, ev, 0));
           }
-          // (overlapped with the next chunk's sort: a push that filled every SM with warps
-          // waiting on NVLink kept the sort kernels out -- two CTAs per SM are enough to keep
-          // the links busy)
+          if (chunks == 1) tr.mark("local_renumber_sort");
+          // one chunk: the rows are pushed in the order of their NEW ids (sorted local index,
+          // scattered local reads of the sorted rows) -- consecutive rows then land at
+          // increasing, mostly adjacent addresses of the same window, and the stores over NVLink
+          // are long runs even when the rows hold 2 entries (source order: 180 GB/s from the
+          // rank with the low-degree rows of R-MAT-26 at 4 GPUs)
+          const I *sidx = nullptr, *dest_id = nullptr;
+          const N *dptr = nullptr;
+          if (chunks == 1 && row_order && mg_push_dest_order()) {
+            using UI = typename std::make_unsigned<I>::type;
+            UI *k0 = ws.alloc<UI>(rows), *i0 = ws.alloc<UI>(rows);
+            UI *k1 = ws.alloc<UI>(rows), *i1 = ws.alloc<UI>(rows);
+            UI *k2 = ws.alloc<UI>(rows), *i2 = ws.alloc<UI>(rows);
+            SB_LAUNCH((mg_order_keys_kernel<I, UI>), (unsigned)ceil_div(rows, 256), 256, 0, st,
+                      (const I *)row_order + lo, rows, k0, i0);
+            radix_sort<UI, UI, NoVal>(ws, {k0, i0, nullptr}, {k1, i1, nullptr}, {k2, i2, nullptr},
+                                      rows, {{0, bits_for((uint64_t)(n > 1 ? n - 1 : 1))}});
+            N *dp = ws.alloc<N>(rows + 1);
+            exclusive_scan<N>(ws, MgWalkLenFn<I, N>{(const N *)sub_ptr, (const I *)i1}, dp, rows);
+            sidx = (const I *)i1;
+            dest_id = (const I *)k1;
+            dptr = dp;
+          }
+          if (chunks == 1) tr.mark("push_order");
+          // (chunks overlapped with the next chunk's sort: a push that filled every SM with
+          // warps waiting on NVLink kept the sort kernels out)
           const int64_t warps = std::min<int64_t>(ceil_div(ents, kMgPushChunk),
                                                   (int64_t)sms * (push_st != st ? 16 : 64));
           SB_LAUNCH((mg_push_rows_kernel<I, N, V>), (unsigned)ceil_div(warps * 32, 256), 256, 0,
                     push_st, c->peers, col_region, val_region, (const N *)sub_ptr,
                     (const I *)(t_col + e0), (const V *)(hv ? t_val + e0 : nullptr),
                     (const I *)row_order, lo + r0, rows, ents, (const N *)new_ptr,
-                    (const int64_t *)nb, (const int64_t *)nb_at);
+                    (const int64_t *)nb, (const int64_t *)nb_at, sidx, dest_id, dptr);
         }
         sub_ptr += rows + 1;
       }
-      tr.mark("local_renumber_sort");
+      if (chunks > 1) tr.mark("local_renumber_sort");
       if (push_st != st) {
         SB_CUDA(cudaEventRecord(ev, push_st));
         SB_CUDA(cudaStreamWaitEvent(st, ev, 0));
@@ -1045,6 +1142,7 @@ int sb200_mg_permute2d_fetch(sb200_mg_comm_t *c, int64_t n, int64_t new_rows, in
     const size_t col_region = lay.take(room * ib);
     const size_t val_region = hv ? lay.take(room * vb) : 0;
     char *mine = c->peers.data(rank);
+    MgTrace tr(c, st, "permute2d_fetch");
     SB_CUDA(cudaMemcpyAsync(out_row_ptr, mine + deg_region, (size_t)(new_rows + 1) * nb,
                             cudaMemcpyDeviceToDevice, st));
     if (new_nnz > 0) {
@@ -1054,7 +1152,9 @@ int sb200_mg_permute2d_fetch(sb200_mg_comm_t *c, int64_t n, int64_t new_rows, in
         SB_CUDA(cudaMemcpyAsync(out_vals, mine + val_region, (size_t)new_nnz * vb,
                                 cudaMemcpyDeviceToDevice, st));
     }
+    tr.mark("copy_out");
     mg_barrier(c, st);  // the window may be reused once every rank has copied its block out
+    tr.mark("barrier");
   });
 }
 
