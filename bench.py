@@ -82,51 +82,104 @@ def ncu_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clocks / throttle reasons of all the job's GPUs sampled DURING the timed region by ONE
+    poller (a thread of rank 0 calling NVML every few milliseconds; `nvidia-smi -lms` as the
+    fallback).  One `nvidia-smi -lms 20` per rank -- eight concurrent pollers -- stalled the CUDA
+    calls of the 8-GPU run for milliseconds at a time (DegreeReorder: 13 ms between the events,
+    2.4 ms inside the operator)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, indices, enabled=True):
+        self.indices = list(indices)
+        self.enabled = enabled
+        self.period_ms = int(os.environ.get("SB200_BENCH_CLOCK_MS", "50"))
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.proc, self.thread, self.stop_flag, self.source = None, None, False, None
+
+    # ---- NVML in-process
+    def _nvml_loop(self, nv, handles):
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            for h in handles:
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:  # noqa: BLE001 -- a failed sample is just a missing sample
+                    pass
+            time.sleep(self.period_ms / 1000.0)
 
     def start(self):
+        if not self.enabled:
+            return
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            handles = [nv.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+            self.mx = [float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)) for h in handles]
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handles), daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.source = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "20"],
+                ["nvidia-smi", "-i", ",".join(map(str, self.indices)), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", str(max(self.period_ms, 50))],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
+    def _read_smi(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for line in self.proc.stdout:
+            r = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
+                self.sm.append(float(r[0]))
+                self.mx.append(float(r[1]))
             except (ValueError, IndexError):
                 continue
             for name, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                    self.reasons.add(name)
+
+    def mark(self):
+        """Samples taken so far (call at the start of the timed region)."""
+        return len(self.sm)
+
+    def stop(self, since=0):
+        if not self.enabled:
+            return None
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        sm = sorted(self.sm)
+        timed = sorted(self.sm[since:])
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None, "samples": len(sm),
+                "samples_in_timed_region": len(timed),
+                "sm_mhz_timed_region": timed[len(timed) // 2] if timed else None,
+                "gpus": self.indices, "period_ms": self.period_ms, "source": self.source,
+                "reasons": sorted(self.reasons)}
 
 
 def dist_env():
@@ -419,9 +472,9 @@ def main():
             record[3].record()
         return inv, (p.bounds[rank], p.bounds[rank + 1]), (p.row_ptr, p.col, p.vals)
 
-    # (clocks are sampled every 20 ms from the warm-up steps on -- the same load -- so that a
-    # timed region of a few tens of milliseconds at 8 GPUs still has samples)
-    sampler = ClockSampler(local_rank)
+    # (clocks are sampled every 50 ms (SB200_BENCH_CLOCK_MS) from the warm-up steps on -- the same
+    # load -- so that a timed region of a few tens of milliseconds at 8 GPUs still has samples)
+    sampler = ClockSampler(range(world), enabled=(rank == 0))
     sampler.start()
     for _ in range(W):
         step()
@@ -429,13 +482,14 @@ def main():
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     barrier()
     lib.reset_launch_count()
+    clock_mark = sampler.mark()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         inv, out_rows, out = step(ev[k])
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = lib.launch_count()
-    clocks = sampler.stop()
+    clocks = sampler.stop(clock_mark)
     ms_per_step = max_over_ranks(ev[0][0].elapsed_time(ev[-1][3]) / args.steps)
     op_ms = {name: max_over_ranks(sum(e[i].elapsed_time(e[i + 1]) for e in ev) / args.steps)
              for i, name in enumerate(("coo_to_csr", "degree_reorder", "permute2d"))}
