@@ -81,87 +81,73 @@ def ncu_traffic():
         return json.load(f).get("permute2d_gather_dram_bytes_per_launch")
 
 
+_POLLER = r"""
+import sys, time
+import pynvml as nv
+idx = [int(x) for x in sys.argv[1].split(',')]
+period = float(sys.argv[2]) / 1000.0
+nv.nvmlInit()
+hs = [nv.nvmlDeviceGetHandleByIndex(i) for i in idx]
+mx = [nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM) for h in hs]
+print('max', *mx, flush=True)
+while True:
+    t = time.time()
+    for i, h in zip(idx, hs):
+        try:
+            print(t, i, nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                  nv.nvmlDeviceGetCurrentClocksThrottleReasons(h), flush=True)
+        except Exception:
+            pass
+    time.sleep(period)
+"""
+
+
 class ClockSampler:
     """SM clocks / throttle reasons of all the job's GPUs sampled DURING the timed region by ONE
-    poller (a thread of rank 0 calling NVML every few milliseconds; `nvidia-smi -lms` as the
-    fallback).  One `nvidia-smi -lms 20` per rank -- eight concurrent pollers -- stalled the CUDA
-    calls of the 8-GPU run for milliseconds at a time (DegreeReorder: 13 ms between the events,
-    2.4 ms inside the operator)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    poller: a child process of rank 0 calling NVML every SB200_BENCH_CLOCK_MS (50) milliseconds;
+    samples carry wall-clock stamps and the timed region is cut out afterwards.  What was tried
+    and dropped: one `nvidia-smi -lms 20` per rank (eight concurrent pollers stalled the CUDA
+    calls of the 8-GPU run for milliseconds at a time: DegreeReorder 13 ms between the events,
+    2.4 ms inside the operator); an NVML thread inside rank 0 (10 ms period: DegreeReorder 0.9 ->
+    5.3 ms at N = 1)."""
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+               "sw_power_cap": 0x4}
 
     def __init__(self, indices, enabled=True):
         self.indices = list(indices)
         self.enabled = enabled
         self.period_ms = int(os.environ.get("SB200_BENCH_CLOCK_MS", "50"))
-        self.sm, self.mx, self.reasons = [], [], set()
-        self.proc, self.thread, self.stop_flag, self.source = None, None, False, None
-
-    # ---- NVML in-process
-    def _nvml_loop(self, nv, handles):
-        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
-                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
-                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
-                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
-        while not self.stop_flag:
-            for h in handles:
-                try:
-                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                    for name, bit in bits.items():
-                        if r & bit:
-                            self.reasons.add(name)
-                except Exception:  # noqa: BLE001 -- a failed sample is just a missing sample
-                    pass
-            time.sleep(self.period_ms / 1000.0)
+        self.rows, self.mx = [], []
+        self.proc, self.thread = None, None
 
     def start(self):
         if not self.enabled:
             return
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            handles = [nv.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
-            self.mx = [float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)) for h in handles]
-            self.source = "nvml"
-            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handles), daemon=True)
-            self.thread.start()
-            return
-        except Exception:  # noqa: BLE001
-            self.source = None
-        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", ",".join(map(str, self.indices)), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", str(max(self.period_ms, 50))],
+                [sys.executable, "-c", _POLLER, ",".join(map(str, self.indices)),
+                 str(self.period_ms)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.source = "nvidia-smi"
-            self.thread = threading.Thread(target=self._read_smi, daemon=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
-    def _read_smi(self):
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    def _read(self):
         for line in self.proc.stdout:
-            r = [x.strip() for x in line.split(",")]
+            f = line.split()
             try:
-                self.sm.append(float(r[0]))
-                self.mx.append(float(r[1]))
+                if f[0] == "max":
+                    self.mx = [float(x) for x in f[1:]]
+                else:
+                    self.rows.append((float(f[0]), int(f[1]), float(f[2]), int(f[3])))
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    self.reasons.add(name)
 
-    def mark(self):
-        """Samples taken so far (call at the start of the timed region)."""
-        return len(self.sm)
-
-    def stop(self, since=0):
+    def stop(self, t0=None, t1=None):
+        """t0, t1 = time.time() at the two ends of the timed region."""
         if not self.enabled:
             return None
-        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
             try:
@@ -170,16 +156,20 @@ class ClockSampler:
                 self.proc.kill()
         if self.thread:
             self.thread.join(timeout=2)
-        if self.source is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
-        sm = sorted(self.sm)
-        timed = sorted(self.sm[since:])
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
-                "sm_max_mhz": max(self.mx) if self.mx else None, "samples": len(sm),
-                "samples_in_timed_region": len(timed),
-                "sm_mhz_timed_region": timed[len(timed) // 2] if timed else None,
-                "gpus": self.indices, "period_ms": self.period_ms, "source": self.source,
-                "reasons": sorted(self.reasons)}
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML samples"]}
+        timed = [r for r in self.rows if t0 is not None and t0 <= r[0] <= t1]
+        use = timed if timed else self.rows
+        sm = sorted(r[2] for r in use)
+        bits = 0
+        for r in use:
+            bits |= r[3]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0],
+                "sm_max_mhz": max(self.mx) if self.mx else None,
+                "samples": len(use), "samples_in_timed_region": len(timed),
+                "samples_total": len(self.rows), "gpus": self.indices,
+                "period_ms": self.period_ms, "source": "NVML poller process of rank 0",
+                "reasons": sorted(k for k, v in self.REASONS.items() if bits & v)}
 
 
 def dist_env():
@@ -424,6 +414,9 @@ def main():
             return float(t.item())
         return x
 
+    # (the clock poller is started here so that it is up and sampling long before the warm-up)
+    sampler = ClockSampler(range(world), enabled=(rank == 0))
+    sampler.start()
     # ---- the matrix (identical on every rank: same generator, same seed, same hardware)
     n, row, col = synth.rmat(args.scale, 8, seed=44, device=dev)
     nnz = col.numel()
@@ -472,24 +465,23 @@ def main():
             record[3].record()
         return inv, (p.bounds[rank], p.bounds[rank + 1]), (p.row_ptr, p.col, p.vals)
 
-    # (clocks are sampled every 50 ms (SB200_BENCH_CLOCK_MS) from the warm-up steps on -- the same
-    # load -- so that a timed region of a few tens of milliseconds at 8 GPUs still has samples)
-    sampler = ClockSampler(range(world), enabled=(rank == 0))
-    sampler.start()
+    # (clocks: samples stamped inside the timed region are reported; when that region is shorter
+    # than the polling period -- 8 GPUs -- all samples since start-up are used and the line
+    # says so in samples_in_timed_region)
     for _ in range(W):
         step()
     # ---- device-resident timing: K steps, CUDA events on the launching stream
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     barrier()
     lib.reset_launch_count()
-    clock_mark = sampler.mark()
+    t_clock0 = time.time()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         inv, out_rows, out = step(ev[k])
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = lib.launch_count()
-    clocks = sampler.stop(clock_mark)
+    clocks = sampler.stop(t_clock0, time.time())
     ms_per_step = max_over_ranks(ev[0][0].elapsed_time(ev[-1][3]) / args.steps)
     op_ms = {name: max_over_ranks(sum(e[i].elapsed_time(e[i + 1]) for e in ev) / args.steps)
              for i, name in enumerate(("coo_to_csr", "degree_reorder", "permute2d"))}
