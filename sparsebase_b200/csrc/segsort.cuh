@@ -80,9 +80,11 @@ struct SsSmem {
   typename std::conditional<has_val<V>, V, char>::type val[has_val<V> ? kSsCap : 1];
   // mark[q]: during the row pass, (q + 1) at the first position of every non-empty segment and
   // 0 elsewhere; after the scan, (start of q's segment + 1) at every position
+  // (mark and base are dead once the gather and the short segments are done: the CTA-wide sort
+  // uses the two arrays, contiguous on purpose, as its exchange area)
   __align__(16) unsigned short mark[kSsCap];
-  unsigned short len[kSsCap];  // at a segment's first position: its length
   N base[kSsCap];              // at a segment's first position: source offset of its entries
+  unsigned short len[kSsCap];  // at a segment's first position: its length
   unsigned mid[kSsMaxMid];     // first positions of the segments with 33..kSsLong entries
   unsigned scratch[kSsBlock / 32];
   unsigned nmid;
@@ -100,6 +102,127 @@ __device__ int64_t ss_segment_of(const N *__restrict__ ptr, int64_t n_seg, int64
       hi = mid;
   }
   return lo - 1;
+}
+
+// Bitonic sorting network over P = T * E (key, value) pairs held in registers: thread t of the
+// group (T = 32: one warp, T = kSsBlock: the CTA) owns the E consecutive elements t * E + i.
+// Comparators between elements of one thread are register moves, between lanes of a warp two
+// shuffles per element, and only the strides that cross warps (CTA version: 6 of the 55 steps
+// at P = 1024) go through shared memory with barriers.  The network this replaced ran every
+// step in shared memory with a barrier (57 warp-instructions per entry of the tile kernel on
+// R-MAT-24, three quarters of them in the compare-exchange loop).
+// Keys are compared as unsigned so that the all-ones padding sorts last; equal keys never swap.
+template <typename U>
+__device__ __forceinline__ U ss_min(U a, U b) {
+  return a < b ? a : b;
+}
+template <typename U>
+__device__ __forceinline__ U ss_max(U a, U b) {
+  return a < b ? b : a;
+}
+template <int E, int T, typename UI, typename VV, bool HV>
+__device__ __forceinline__ void ss_bitonic_regs(UI (&key)[E], VV (&val)[E], int t, UI *xk,
+                                                VV *xv) {
+  constexpr int P = T * E;
+#pragma unroll 1
+  for (int k = 2; k <= P; k <<= 1) {
+    const bool asc_t = ((t * E) & k) == 0;  // direction of this thread's elements when k >= 2E
+    int j = k >> 1;
+    if constexpr (T > 32) {
+#pragma unroll 1
+      for (; j >= 32 * E; j >>= 1) {  // partner in another warp
+        const int tm = j / E;
+        const int tp = t ^ tm;
+        __syncthreads();  // (the readers of the previous exchange are done)
+#pragma unroll
+        for (int i = 0; i < E; i++) {
+          xk[t * E + i] = key[i];
+          if constexpr (HV) xv[t * E + i] = val[i];
+        }
+        __syncthreads();
+        const UI m_min = (((t & tm) == 0) == asc_t) ? ~(UI)0 : (UI)0;  // all ones: I keep the min
+#pragma unroll
+        for (int i = 0; i < E; i++) {
+          const UI pk = xk[tp * E + i];
+          // (min / max + a bit mask, not comparisons under a condition: nvcc turned those into
+          // divergent branches around every shuffle)
+          const UI nk = (ss_min(key[i], pk) & m_min) | (ss_max(key[i], pk) & ~m_min);
+          if constexpr (HV) {
+            const VV pv = xv[tp * E + i];
+            val[i] = nk != key[i] ? pv : val[i];
+          }
+          key[i] = nk;
+        }
+      }
+    }
+#pragma unroll 1
+    for (; j >= E; j >>= 1) {  // partner in another lane of the warp
+      const int lm = j / E;
+      const UI m_min = (((t & lm) == 0) == asc_t) ? ~(UI)0 : (UI)0;
+#pragma unroll
+      for (int i = 0; i < E; i++) {
+        const UI pk = __shfl_xor_sync(0xffffffffu, key[i], lm);
+        [[maybe_unused]] VV pv = val[i];
+        if constexpr (HV) pv = __shfl_xor_sync(0xffffffffu, val[i], lm);
+        const UI nk = (ss_min(key[i], pk) & m_min) | (ss_max(key[i], pk) & ~m_min);
+        if constexpr (HV) val[i] = nk != key[i] ? pv : val[i];
+        key[i] = nk;
+      }
+    }
+#pragma unroll
+    for (int jj = E / 2; jj >= 1; jj >>= 1) {  // partner in my own registers
+      if (jj < k) {
+#pragma unroll
+        for (int i = 0; i < E; i++) {
+          const int p2 = i ^ jj;
+          if (p2 > i) {
+            const bool asc = ((t * E + i) & k) == 0;
+            const UI ka = key[i], kb = key[p2];
+            const UI m_asc = asc ? ~(UI)0 : (UI)0;
+            const UI lo = ss_min(ka, kb), hi = ss_max(ka, kb);
+            key[i] = (lo & m_asc) | (hi & ~m_asc);
+            key[p2] = (hi & m_asc) | (lo & ~m_asc);
+            if constexpr (HV) {
+              const bool sw = key[i] != ka;
+              const VV va = val[i], vb = val[p2];
+              val[i] = sw ? vb : va;
+              val[p2] = sw ? va : vb;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// Sorts the `len` entries at skey / sval (shared memory) with the network above: loads them
+// into registers (padding up to T * E), sorts, writes them back.  The caller synchronises.
+template <int E, int T, typename I, typename VV, bool HV>
+__device__ __forceinline__ void ss_sort_in_regs(I *skey, VV *sval, int len, int t, void *xch) {
+  using UI = typename std::make_unsigned<I>::type;
+  UI key[E];
+  VV val[E];
+#pragma unroll
+  for (int i = 0; i < E; i++) {
+    const int idx = t * E + i;
+    key[i] = idx < len ? (UI)skey[idx] : ~(UI)0;
+    if constexpr (HV) {
+      val[i] = idx < len ? sval[idx] : VV();
+    } else {
+      val[i] = VV();
+    }
+  }
+  UI *xk = reinterpret_cast<UI *>(xch);
+  VV *xv = reinterpret_cast<VV *>(reinterpret_cast<unsigned char *>(xch) + (size_t)T * E * sizeof(UI));
+  ss_bitonic_regs<E, T, UI, VV, HV>(key, val, t, xk, xv);
+#pragma unroll
+  for (int i = 0; i < E; i++) {
+    const int idx = t * E + i;
+    if (idx < len) {
+      skey[idx] = (I)key[i];
+      if constexpr (HV) sval[idx] = val[i];
+    }
+  }
 }
 
 // Loader concept:  int64_t seg_base(int64_t seg)  source offset of the segment's first entry
@@ -268,14 +391,15 @@ __global__ void __launch_bounds__(kSsBlock)
     for (int x = lane + 1; x < len; x += 32)
       if (key[x - 1] > key[x]) unsorted = true;
     __syncwarp();
-    int P = 64;
-    while (P < len) P <<= 1;
-    for (int k = 2; k <= P; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int x = lane; x < (P >> 1); x += 32) compare_exchange(key, sb, len, k, j, x);
-        __syncwarp();
-      }
+    {
+      using VV = typename std::conditional<has_val<V>, V, char>::type;
+      VV *sval = reinterpret_cast<VV *>(s.val) + (has_val<V> ? sb : 0);
+      if (len <= 64)
+        ss_sort_in_regs<2, 32, I, VV, has_val<V>>(key, sval, len, (int)lane, nullptr);
+      else
+        ss_sort_in_regs<4, 32, I, VV, has_val<V>>(key, sval, len, (int)lane, nullptr);
     }
+    __syncwarp();
     bool dup = false;
     for (int x = lane; x < len; x += 32) {
       if (x + 1 < len && key[x] == key[x + 1]) dup = true;
@@ -294,12 +418,29 @@ __global__ void __launch_bounds__(kSsBlock)
     for (int x = threadIdx.x + 1; x < len; x += kSsBlock)
       if (key[x - 1] > key[x]) unsorted = true;
     __syncthreads();
-    int P = 256;
-    while (P < len) P <<= 1;
-    for (int k = 2; k <= P; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int x = threadIdx.x; x < (P >> 1); x += kSsBlock) compare_exchange(key, sb, len, k, j, x);
-        __syncthreads();
+    using VV = typename std::conditional<has_val<V>, V, char>::type;
+    constexpr size_t kXchBytes = sizeof(s.mark) + sizeof(s.base);
+    constexpr bool kRegsFit =
+        (size_t)kSsLong * (sizeof(I) + (has_val<V> ? sizeof(V) : 0)) <= kXchBytes;
+    if constexpr (kRegsFit) {
+      VV *sval = reinterpret_cast<VV *>(s.val) + (has_val<V> ? sb : 0);
+      void *xch = s.mark;  // mark + base: dead since the barrier above
+      if (len <= 256)
+        ss_sort_in_regs<1, kSsBlock, I, VV, has_val<V>>(key, sval, len, (int)threadIdx.x, xch);
+      else if (len <= 512)
+        ss_sort_in_regs<2, kSsBlock, I, VV, has_val<V>>(key, sval, len, (int)threadIdx.x, xch);
+      else
+        ss_sort_in_regs<4, kSsBlock, I, VV, has_val<V>>(key, sval, len, (int)threadIdx.x, xch);
+      __syncthreads();
+    } else {  // (64-bit ids with 32-bit offsets: the exchange area is too small)
+      int P = 256;
+      while (P < len) P <<= 1;
+      for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int x = threadIdx.x; x < (P >> 1); x += kSsBlock)
+            compare_exchange(key, sb, len, k, j, x);
+          __syncthreads();
+        }
       }
     }
     bool dup = false;
