@@ -267,6 +267,18 @@ int sb200_degree_rank_combine(int device, int64_t n, const void *row_ptr, const 
                               int nnz_type, void *stream);
 
 
+/* reorder::ReorderHeatmap::ReorderHeatmapCSRArrayArray (reorder/reorder_heatmap.cc:43-120):
+ * out_heat[num_parts * num_parts] (device, feature_type) = share of the nonzeros that fall into
+ * every cell of a num_parts x num_parts grid once rows / columns are renumbered by order_r[n] /
+ * order_c[m] (order[i] = new position of i; NULL = identity).  Blocks hold n / num_parts rows and
+ * columns, the last one takes the remainder; the division is a float division as in the
+ * reference.  SB200_ERR_BAD_ARG where the reference throws ReorderException (num_parts larger
+ * than a dimension). */
+int sb200_reorder_heatmap(int device, int64_t n, int64_t m, int64_t nnz, const void *row_ptr,
+                          const void *col, const void *order_r, const void *order_c,
+                          int num_parts, void *out_heat, int id_type, int nnz_type,
+                          int feature_type, void *stream);
+
 /* ---- multi-GPU: row-block sharded operators over peer memory ----
  *
  * The reference has no distributed code (its "multi-GPU" is the peer copy of

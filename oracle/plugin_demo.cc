@@ -188,6 +188,21 @@ static void run_case(const char *name, Coo c, context::CPUContext &cpu, context:
   I *g_got = dg.GetDegrees(dcsr, {&gpu}, false);
   CHECK(same(g_ref, g_got, n), "Degrees");
 
+  // ---- ReorderHeatmap (rows and columns renumbered by the RCM permutation)
+  STEP("ReorderHeatmap");
+  {
+    reorder::ReorderHeatmap<I, N, V, float> hm{reorder::ReorderHeatmapParams(7)};
+    sb200_plugin::Register(hm);
+    format::Array<I> perm_h(n, rcm_ref, format::kNotOwned);
+    auto *h_ref = hm.Get(csr_ref, &perm_h, &perm_h, {&cpu}, false)->As<format::Array>();
+    auto *perm_d = perm_h.Convert<format::CUDAArray>(&gpu);
+    auto *h_got = hm.Get(dcsr, perm_d, perm_d, {&gpu}, false)->As<format::Array>();
+    CHECK(same(h_ref->get_vals(), h_got->get_vals(), 49), "ReorderHeatmap<float> 7x7");
+    delete h_got;
+    delete perm_d;
+    delete h_ref;
+  }
+
   STEP("cleanup");
   delete[] d_ref;
   delete[] d_got;

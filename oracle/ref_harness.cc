@@ -76,6 +76,7 @@ void operator delete[](void *p, std::size_t) noexcept { std::free(p); }
 #include "sparsebase/io/edge_list_reader.h"
 #include "sparsebase/reorder/degree_reorder.h"
 #include "sparsebase/reorder/rcm_reorder.h"
+#include "sparsebase/reorder/reorder_heatmap.h"
 #include "sparsebase/utils/logger.h"
 
 using namespace sparsebase;
@@ -253,6 +254,25 @@ int degree_distribution(int64_t n, int64_t m, N *row_ptr, I *col, V *vals, F *o_
   return 0;
 }
 
+// reorder::ReorderHeatmap (reorder/reorder_heatmap.cc:43-120) with num_parts = b.  Returns 1
+// where the reference throws (b larger than a dimension).
+template <typename I, typename N, typename V, typename F>
+int reorder_heatmap(int64_t n, int64_t m, N *row_ptr, I *col, I *order_r, I *order_c, int b,
+                    F *out_heat) {
+  format::CSR<I, N, V> csr((I)n, (I)m, row_ptr, col, (V *)nullptr, format::kNotOwned, true);
+  format::Array<I> pr((I)n, order_r, format::kNotOwned), pc((I)m, order_c, format::kNotOwned);
+  reorder::ReorderHeatmap<I, N, V, F> h{reorder::ReorderHeatmapParams(b)};
+  try {
+    auto *res = h.Get(&csr, &pr, &pc, {&g_cpu}, true);
+    auto *arr = res->template AsAbsolute<format::Array<F>>();
+    copy_out(out_heat, arr->get_vals(), (size_t)b * b);
+    delete res;
+  } catch (utils::ReorderException &) {
+    return 1;
+  }
+  return 0;
+}
+
 // Fused degree features + the quality metrics of a reordering, through the reference's own
 // feature classes.  out_scalars = {min_degree, max_degree, bandwidth, profile}.
 template <typename I, typename N, typename V, typename F>
@@ -392,6 +412,11 @@ int edges_to_coo(int64_t n_edges, I *u, I *v, V *w, int remove_duplicates, int r
                                   void *odist, int64_t *out4, void *oavg) {                  \
     return degree_features<I, N, V, F>(n, m, (N *)rp, (I *)col, (I *)odeg, (F *)odist, out4, \
                                        (F *)oavg);                                           \
+  }                                                                                          \
+  int sbref_reorder_heatmap_##TAG(int64_t n, int64_t m, void *rp, void *col, void *pr,       \
+                                  void *pc, int b, void *oheat) {                            \
+    return reorder_heatmap<I, N, V, F>(n, m, (N *)rp, (I *)col, (I *)pr, (I *)pc, b,         \
+                                       (F *)oheat);                                          \
   }                                                                                          \
   int sbref_edges_to_coo_##TAG(int64_t ne, void *u, void *v, void *w, int rd, int rs, int un,\
                                int sq, void *orow, void *ocol, void *ovals, int64_t *out3) { \

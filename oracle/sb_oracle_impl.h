@@ -537,6 +537,37 @@ int FN(degree_features)(int64_t n, int64_t m, void *rp_, void *col_, void *odeg_
   return 0;
 }
 
+/* reorder/reorder_heatmap.cc:43-120 -- ReorderHeatmapCSRArrayArray: the b x b grid of nonzero
+ * densities of the matrix as it would look after the row / column permutations (order[i] = new
+ * position of i): bsize = n / b for BOTH dimensions (:62), block index clamped to b - 1
+ * (:73-74, :83-84), heat[i * b + j] = density / (row_ptr[n] + .0f) -- a FLOAT division whatever
+ * FloatType is (:112), then converted.  Returns 1 where the reference throws (b > n or b > m,
+ * :52-56). */
+int FN(reorder_heatmap)(int64_t n, int64_t m, void *rp_, void *col_, void *order_r_,
+                        void *order_c_, int b, void *out_heat_) {
+  const N *rows = (const N *)rp_;
+  const I *col = (const I *)col_;
+  const I *order_r = (const I *)order_r_, *order_c = (const I *)order_c_;
+  F *heat = (F *)out_heat_;
+  if (b < 1 || b > n || b > m) return 1;
+  const I bsize = (I)(n / b);
+  N *density = (N *)calloc((size_t)b * b, sizeof(N));
+  for (int64_t i = 0; i < n; i++) {
+    I u = order_r[i];
+    I bu = u / bsize;
+    if (bu >= b) bu = (I)(b - 1);
+    for (N k = rows[i]; k < rows[i + 1]; k++) {
+      I v = order_c[col[k]];
+      I bv = v / bsize;
+      if (bv >= b) bv = (I)(b - 1);
+      density[(size_t)bu * b + bv]++;
+    }
+  }
+  for (int64_t k = 0; k < (int64_t)b * b; k++) heat[k] = (F)(density[k] / (rows[n] + .0f));
+  free(density);
+  return 0;
+}
+
 /* io/edge_list_reader.cc:28-151 -- EdgeListReader::ReadCOO on an in-memory edge list:
  * self edges dropped when remove_self (:40 / :98), the reverse edge pushed right behind
  * every kept edge when undirected (:43-44 / :101-102), n = max u + 1, m = max v + 1 over the

@@ -283,6 +283,109 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------ ReorderHeatmap
+// reorder/reorder_heatmap.cc:43-120: density[bu][bv] counts the nonzeros whose permuted
+// coordinates (order_r[i], order_c[col]) fall into block (bu, bv) of a b x b grid with
+// bsize = n / b rows AND columns per block (the last block takes the remainder).
+// Work is dealt out by ENTRIES (4096 per warp), as in the row push of the sharded Permute2D: a
+// power-law matrix keeps its heavy rows next to each other.  Lane l resolves row l of the current
+// batch of 32 rows (its block row, its clipped extent), then the warp walks the batch's
+// concatenated entries 32 at a time.  Counts go to a CTA-private histogram in shared memory when
+// the grid has at most kHeatShared cells, else straight to global memory.
+constexpr int kHeatShared = 4096;
+constexpr int64_t kHeatChunk = 4096;
+template <typename I, typename N>
+__global__ void __launch_bounds__(256)
+    heatmap_count_kernel(const N *__restrict__ row_ptr, const I *__restrict__ col,
+                         const I *__restrict__ order_r, const I *__restrict__ order_c, int64_t n,
+                         int64_t nnz, unsigned long long bsize, int b,
+                         unsigned long long *__restrict__ density) {
+  __shared__ unsigned sh[kHeatShared];
+  const int cells = b * b;
+  const bool priv = cells <= kHeatShared;
+  if (priv) {
+    for (int k = threadIdx.x; k < cells; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+  }
+  const unsigned lane = lane_id();
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t nchunks = (nnz + kHeatChunk - 1) / kHeatChunk;
+  for (int64_t w = warp; w < nchunks; w += nwarps) {
+    const int64_t e0 = w * kHeatChunk;
+    const int64_t e1 = e0 + kHeatChunk < nnz ? e0 + kHeatChunk : nnz;
+    int64_t lo = 0, hi = n;  // last row with row_ptr[row] <= e0
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)row_ptr[mid] <= e0)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    for (int64_t g = lo; g < n; g += 32) {
+      const int64_t i = g + lane;
+      int64_t bgn = 0;
+      unsigned d = 0, bu = 0;
+      int64_t next_begin = nnz;
+      if (i < n) {
+        const int64_t rb = (int64_t)row_ptr[i], re = (int64_t)row_ptr[i + 1];
+        next_begin = re;
+        bgn = rb > e0 ? rb : e0;
+        const int64_t e = re < e1 ? re : e1;
+        if (e > bgn) {
+          d = (unsigned)(e - bgn);
+          const unsigned long long u = (unsigned long long)(order_r ? order_r[i] : (I)i);
+          const unsigned long long q = u / bsize;
+          bu = (unsigned)(q >= (unsigned long long)b ? b - 1 : q);
+        }
+      }
+      const unsigned incl = warp_inclusive_scan(d);
+      const unsigned excl = incl - d;
+      const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
+      for (unsigned base = 0; base < tot; base += 32) {
+        const unsigned s = base + lane;
+        unsigned own = 0;  // number of lanes whose inclusive end <= s == owner lane
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const unsigned val = __shfl_sync(0xffffffffu, incl, (own + step - 1) & 31);
+          if (val <= s) own += step;
+        }
+        const unsigned j = own & 31;
+        const int64_t bgn_j = __shfl_sync(0xffffffffu, bgn, j);
+        const unsigned excl_j = __shfl_sync(0xffffffffu, excl, j);
+        const unsigned bu_j = __shfl_sync(0xffffffffu, bu, j);
+        if (s < tot) {
+          const I c = ld_stream(col + bgn_j + (s - excl_j));
+          const unsigned long long v = (unsigned long long)(order_c ? __ldg(order_c + c) : c);
+          const unsigned long long q = v / bsize;
+          const unsigned bv = (unsigned)(q >= (unsigned long long)b ? b - 1 : q);
+          const unsigned cell = bu_j * (unsigned)b + bv;
+          if (priv)
+            atomicAdd(&sh[cell], 1u);
+          else
+            atomicAdd(&density[cell], 1ull);
+        }
+      }
+      if (__shfl_sync(0xffffffffu, next_begin, 31) >= e1) break;
+    }
+  }
+  if (priv) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < cells; k += blockDim.x)
+      if (sh[k]) atomicAdd(&density[k], (unsigned long long)sh[k]);
+  }
+}
+// heat = density / (row_ptr[n] + .0f): a FLOAT division whatever FloatType is (:112)
+template <typename N, typename F>
+__global__ void heatmap_finish_kernel(const unsigned long long *__restrict__ density,
+                                      const N *__restrict__ row_ptr, int64_t n, int cells,
+                                      F *__restrict__ heat) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cells) return;
+  const float total = (float)row_ptr[n];
+  heat[k] = (F)__fdiv_rn((float)(N)density[k], total);
+}
+
 }  // namespace sb200
 
 using namespace sb200;
@@ -362,6 +465,48 @@ int sb200_degree_features(int device, int64_t n, int64_t nnz, const void *row_pt
       else
         *h_out_avg = (double)(h_last - h_first) / (double)n;
     }
+  });
+}
+
+int sb200_reorder_heatmap(int device, int64_t n, int64_t m, int64_t nnz, const void *row_ptr,
+                          const void *col, const void *order_r, const void *order_c,
+                          int num_parts, void *out_heat, int id_type, int nnz_type,
+                          int feature_type, void *stream) {
+  return guarded(device, [&] {
+    SB_REQUIRE(n >= 0 && m >= 0 && nnz >= 0 && out_heat && (n == 0 || row_ptr) &&
+                   (nnz == 0 || col),
+               SB200_ERR_BAD_ARG, "bad argument");
+    SB_REQUIRE(feature_type == SB200_F32 || feature_type == SB200_F64, SB200_ERR_BAD_DTYPE,
+               "feature_type must be F32 or F64");
+    // reorder_heatmap.cc:52-56
+    SB_REQUIRE(num_parts >= 1 && num_parts <= n && num_parts <= m, SB200_ERR_BAD_ARG,
+               "Cannot generate heatmap for matrix when num_parts > number of rows or columns");
+    SB_REQUIRE(num_parts <= 46340, SB200_ERR_BAD_ARG, "num_parts * num_parts must fit in an int");
+    Workspace ws(device, (cudaStream_t)stream);
+    cudaStream_t st = ws.stream();
+    const int cells = num_parts * num_parts;
+    unsigned long long *density = ws.alloc<unsigned long long>(cells);
+    SB_CUDA(cudaMemsetAsync(density, 0, (size_t)cells * sizeof(unsigned long long), st));
+    dispatch_inv(id_type, nnz_type, SB200_VOID, false, [&](auto I_, auto N_, auto) {
+      using I = decltype(I_);
+      using N = decltype(N_);
+      if (nnz > 0) {
+        const int64_t warps = ceil_div(nnz, kHeatChunk);
+        const int64_t cap = (int64_t)device_info(device).sm_count * 8;
+        const int64_t blocks = ceil_div(warps, 8);
+        SB_LAUNCH((heatmap_count_kernel<I, N>), (unsigned)(blocks < cap ? blocks : cap), 256, 0, st,
+                  (const N *)row_ptr, (const I *)col, (const I *)order_r, (const I *)order_c, n,
+                  nnz, (unsigned long long)(n / num_parts), num_parts, density);
+      }
+      if (feature_type == SB200_F32)
+        SB_LAUNCH((heatmap_finish_kernel<N, float>), (unsigned)ceil_div(cells, 256), 256, 0, st,
+                  (const unsigned long long *)density, (const N *)row_ptr, n, cells,
+                  (float *)out_heat);
+      else
+        SB_LAUNCH((heatmap_finish_kernel<N, double>), (unsigned)ceil_div(cells, 256), 256, 0, st,
+                  (const unsigned long long *)density, (const N *)row_ptr, n, cells,
+                  (double *)out_heat);
+    });
   });
 }
 

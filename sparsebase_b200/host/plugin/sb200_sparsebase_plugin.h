@@ -45,6 +45,7 @@
 #include "sparsebase/permute/permute_order_two.h"
 #include "sparsebase/reorder/degree_reorder.h"
 #include "sparsebase/reorder/rcm_reorder.h"
+#include "sparsebase/reorder/reorder_heatmap.h"
 
 namespace sb200_plugin {
 namespace sbase = ::sparsebase;
@@ -499,7 +500,41 @@ I *DegreesCUDACSR(std::vector<sbase::format::Format *> formats, sbase::utils::Pa
   return h;
 }
 
+// reorder::ReorderHeatmap on {CUDACSR, CUDAArray, CUDAArray} (the reference registers
+// {CSR, Array, Array}, reorder/reorder_heatmap.cc:11-15).  The grid is small: it comes back as
+// a host Array, the type the reference's own function returns.
+template <typename I, typename N, typename V, typename F>
+sbase::format::FormatOrderOne<F> *ReorderHeatmapCUDACSR(
+    std::vector<sbase::format::Format *> formats, sbase::utils::Parameters *params) {
+  auto *csr = formats[0]->AsAbsolute<sbase::format::CUDACSR<I, N, V>>();
+  auto *pr = formats[1]->AsAbsolute<sbase::format::CUDAArray<I>>();
+  auto *pc = formats[2]->AsAbsolute<sbase::format::CUDAArray<I>>();
+  auto *p = static_cast<sbase::reorder::ReorderHeatmapParams *>(params);
+  const int dev = csr->get_cuda_context()->device_id;
+  const auto dims = csr->get_dimensions();
+  const int b = p->num_parts;
+  if (b < 1 || (size_t)b > dims[0] || (size_t)b > dims[1])
+    throw sbase::utils::ReorderException(
+        "Cannot generate heatmap for matrix when num_parts > number of rows or columns");
+  F *d_heat = dev_alloc<F>(dev, (size_t)b * b);
+  const int rc = sb200_reorder_heatmap(dev, dims[0], dims[1], csr->get_num_nnz(),
+                                       csr->get_row_ptr(), csr->get_col(), pr->get_vals(),
+                                       pc->get_vals(), b, d_heat, dtype_of<I>(), dtype_of<N>(),
+                                       dtype_of<F>(), nullptr);
+  F *h = rc == SB200_OK ? to_host(dev, d_heat, (size_t)b * b) : nullptr;
+  dev_free(dev, d_heat);
+  check(rc, dev);
+  return new sbase::format::Array<F>((size_t)b * b, h, sbase::format::kOwned);
+}
+
 // ------------------------------------------------------------------ registration helpers
+template <typename I, typename N, typename V, typename F>
+void Register(sbase::reorder::ReorderHeatmap<I, N, V, F> &op) {
+  op.RegisterFunction({sbase::format::CUDACSR<I, N, V>::get_id_static(),
+                       sbase::format::CUDAArray<I>::get_id_static(),
+                       sbase::format::CUDAArray<I>::get_id_static()},
+                      ReorderHeatmapCUDACSR<I, N, V, F>);
+}
 template <typename I, typename N, typename V>
 void Register(sbase::reorder::DegreeReorder<I, N, V> &op) {
   op.RegisterFunction({sbase::format::CUDACSR<I, N, V>::get_id_static()}, DegreeReorderCUDACSR<I, N, V>);

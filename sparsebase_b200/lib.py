@@ -27,7 +27,7 @@ SYMBOLS = [
     "sb200_rcm_last_resplits",
     "sb200_rcm_last_speculation", "sb200_permute2d", "sb200_permute1d",
     "sb200_inverse_permutation",
-    "sb200_degrees", "sb200_degree_distribution", "sb200_degree_features", "sb200_edges_to_coo", "sb200_partition_rows", "sb200_launch_count",
+    "sb200_degrees", "sb200_degree_distribution", "sb200_degree_features", "sb200_reorder_heatmap", "sb200_edges_to_coo", "sb200_partition_rows", "sb200_launch_count",
     "sb200_reset_launch_count", "sb200_coo_to_csr_block", "sb200_csr_to_csc_block",
     "sb200_exclusive_scan", "sb200_rank_keys", "sb200_max_degree", "sb200_degree_histogram",
     "sb200_degree_rank_combine",
@@ -275,6 +275,20 @@ def degree_features(n, nnz, row_ptr, col=None, id_dtype=torch.int32,
     out = dict(zip(("min_degree", "max_degree", "bandwidth", "profile"), (int(x) for x in sc)))
     out["avg_degree"] = avg.value
     return deg, dist, out
+
+
+def reorder_heatmap(n, m, row_ptr, col, order_r, order_c, num_parts=3,
+                    feature_dtype=torch.float32):
+    """ReorderHeatmap: num_parts x num_parts grid (row-major, device tensor) of the shares of the
+    nonzeros per cell after renumbering rows / columns by order_r / order_c (None = identity).
+    Raises Sb200Error (BAD_ARG) where the reference throws (num_parts > n or m)."""
+    heat = torch.empty(max(1, num_parts * num_parts), dtype=feature_dtype, device=row_ptr.device)
+    _check(load().sb200_reorder_heatmap(_dev(row_ptr), _i64(n), _i64(m), _i64(col.numel()),
+                                        _p(row_ptr), _p(col), _p(order_r), _p(order_c),
+                                        ctypes.c_int(num_parts), _p(heat), _DT[col.dtype],
+                                        _DT[row_ptr.dtype], _DT[feature_dtype],
+                                        _stream(row_ptr)))
+    return heat[:num_parts * num_parts]
 
 
 def edges_to_coo(u, v, w=None, remove_duplicates=True, remove_self_edges=False,

@@ -213,6 +213,21 @@ class Oracle:
         return deg, dist, dict(zip(("min_degree", "max_degree", "bandwidth", "profile"),
                                    (int(x) for x in sc))), avg[0]
 
+    def reorder_heatmap(self, n, row_ptr, col, order_r, order_c, num_parts,
+                        vals_dtype=np.float32):
+        """ReorderHeatmap: the num_parts x num_parts density grid (FeatureType of the type set),
+        or None where the reference throws (num_parts larger than a dimension)."""
+        row_ptr, col, order_r, order_c = _c(row_ptr), _c(col), _c(order_r), _c(order_c)
+        t = tag_of(col.dtype, row_ptr.dtype, vals_dtype)
+        out = np.zeros(max(1, num_parts * num_parts), _FEAT[t])
+        rc = self._fn(f"reorder_heatmap_{t}")(self._i64(n), self._i64(n), _ptr(row_ptr),
+                                              _ptr(col), _ptr(order_r), _ptr(order_c),
+                                              ctypes.c_int(num_parts), _ptr(out))
+        if rc == 1:
+            return None
+        assert rc == 0
+        return out[:num_parts * num_parts]
+
     def edges_to_coo(self, u, v, w=None, remove_duplicates=True, remove_self=False,
                      undirected=False, square=False, nnz_dtype=np.int32):
         """EdgeListReader::ReadCOO semantics on arrays: returns (n, m, row, col, vals)."""

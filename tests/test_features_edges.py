@@ -3,6 +3,7 @@
 * edge list -> sorted, de-duplicated COO   io/edge_list_reader.cc:28-151
 * fused degree features + Bandwidth + Profile   feature/degrees_degree_distribution.cc:147-166,
   feature/min_max_avg_degree.cc:168-191, feature/bandwidth.cc:92-111, feature/profile.cc:92-106
+* ReorderHeatmap (rank 3)   reorder/reorder_heatmap.cc:43-120
 
 CPU part: the restated oracle against the compiled reference (the reference's EdgeListReader
 reads a text file the harness writes) and against the reference's own golden vectors
@@ -117,6 +118,44 @@ def test_degree_features_reference_goldens():
 
 
 # ------------------------------------------------------------------ GPU
+HEAT_PARTS = (1, 2, 3, 7, 64, 100)
+
+
+def heat_orders(n, idt, seed):
+    rng = np.random.default_rng(seed)
+    return rng.permutation(n).astype(idt), rng.permutation(n).astype(idt)
+
+
+def test_reorder_heatmap_reference_goldens():
+    """tests/suites/sparsebase/reorder/reorder_heatmap_tests.cc:25-82 (Instance,
+    InstanceTwoReorders, InstanceDefaultConstructor: num_parts = 3) with the vectors of
+    functionality_common.inc:6-52."""
+    orc = oracle_lib.restated()
+    rp = np.array([0, 2, 3, 4], np.int32)
+    col = np.array([1, 2, 0, 0], np.int32)
+    ident = np.arange(3, dtype=np.int32)
+    no_order = np.array([0, 0.25, 0.25, 0.25, 0, 0, 0.25, 0, 0], np.float32)
+    rc_order = np.array([0, 0, 0.25, 0.25, 0.25, 0, 0, 0, 0.25], np.float32)
+    assert eq(orc.reorder_heatmap(3, rp, col, ident, ident, 3), no_order)
+    r_vec, c_vec = np.array([1, 2, 0], np.int32), np.array([2, 0, 1], np.int32)
+    assert eq(orc.reorder_heatmap(3, rp, col, r_vec, c_vec, 3), rc_order)
+    assert orc.reorder_heatmap(3, rp, col, ident, ident, 4) is None  # the reference throws
+
+
+@needs_ref
+def test_reorder_heatmap_restated_equals_reference():
+    orc, ref = oracle_lib.restated(), oracle_lib.reference()
+    for name, n, rp, col in feature_graphs():
+        for idt, nt, vt in ((np.int32, np.int32, np.float32), (np.int64, np.int64, np.float64),
+                            (np.int32, np.int64, np.float32)):
+            rp2, col2 = rp.astype(nt), col.astype(idt)
+            pr, pc = heat_orders(n, idt, 11)
+            for b in HEAT_PARTS + (n, n + 1):
+                a = orc.reorder_heatmap(n, rp2, col2, pr, pc, b, vt)
+                e = ref.reorder_heatmap(n, rp2, col2, pr, pc, b, vt)
+                assert eq(a, e), (name, idt, b)
+
+
 @pytest.fixture(scope="module")
 def sb():
     from sparsebase_b200 import lib
@@ -181,3 +220,34 @@ def test_degree_features_gpu(sb):
     name, n, rp, col = feature_graphs()[0]
     _, _, sc = sb.degree_features(n, len(col), dev(rp), dev(col), want_arrays=False)
     assert sc["bandwidth"] == orc.degree_features(n, rp, col)[2]["bandwidth"]
+
+
+@pytest.mark.gpu
+def test_reorder_heatmap_gpu(sb):
+    """sb200_reorder_heatmap against the oracle: shared-memory grid (num_parts <= 64), global
+    grid (100), one cell, one row per block (num_parts = n), identity orders, 64-bit types, and
+    the reference's exception."""
+    from sparsebase_b200.lib import Sb200Error
+    orc = oracle_lib.restated()
+    for name, n, rp, col in feature_graphs():
+        for idt, nt, vt, tft in ((np.int32, np.int32, np.float32, torch.float32),
+                                 (np.int64, np.int64, np.float64, torch.float64),
+                                 (np.int32, np.int64, np.float32, torch.float32)):
+            rp2, col2 = rp.astype(nt), col.astype(idt)
+            pr, pc = heat_orders(n, idt, 11)
+            for b in HEAT_PARTS + ((n,) if n <= 2000 else ()):
+                exp = orc.reorder_heatmap(n, rp2, col2, pr, pc, b, vt)
+                got = sb.reorder_heatmap(n, n, dev(rp2), dev(col2), dev(pr), dev(pc), b, tft)
+                assert eq(host(got), exp), (name, idt, b)
+            ident = np.arange(n, dtype=idt)
+            exp = orc.reorder_heatmap(n, rp2, col2, ident, ident, 5, vt)
+            got = sb.reorder_heatmap(n, n, dev(rp2), dev(col2), None, None, 5, tft)
+            assert eq(host(got), exp), (name, "identity")
+    name, n, rp, col = feature_graphs()[0]
+    with pytest.raises(Sb200Error):
+        sb.reorder_heatmap(n, n, dev(rp), dev(col), None, None, n + 1)
+    # a heavier matrix: hub rows spanning many 4096-entry chunks
+    n, r, c = graphs.rmat(15, 8, seed=21)
+    rp, pr = graphs.csr_of(n, r, c), sb.degree_reorder(n, dev(graphs.csr_of(n, r, c)), True)
+    exp = orc.reorder_heatmap(n, rp, c, host(pr), host(pr), 16)
+    assert eq(host(sb.reorder_heatmap(n, n, dev(rp), dev(c), pr, pr, 16)), exp)
