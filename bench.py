@@ -332,6 +332,17 @@ def rcm_block(lib, dev, peak, grid=4096, reps=3):
     st = lib.rcm_last_stats()
     _, _, before = lib.degree_features(n, nnz, rp, col, want_arrays=False)
     _, _, after = lib.degree_features(n, nnz, out[0], out[1], want_arrays=False)
+    # ReorderHeatmap (8 x 8) of the matrix as it is and as the RCM permutation arranges it
+    hb = 8
+    heat0 = lib.reorder_heatmap(n, n, rp, col, None, None, hb)
+    hev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    hev[0].record()
+    heat1 = lib.reorder_heatmap(n, n, rp, col, inv, inv, hb)
+    hev[1].record()
+    torch.cuda.synchronize()
+    heatmap = {"num_parts": hb, "ms": hev[0].elapsed_time(hev[1]),
+               "diagonal_share_before": float(heat0.view(hb, hb).diagonal().sum()),
+               "diagonal_share_after": float(heat1.view(hb, hb).diagonal().sum())}
     ref, kind, _ = _oracle()
     h = [t.cpu().numpy() for t in (rp, col, vals)]
     t0 = time.perf_counter()
@@ -366,6 +377,7 @@ def rcm_block(lib, dev, peak, grid=4096, reps=3):
             "bfs": st["bfs"], "cluster_resizes": st["resizes"], "share_resplits": st["resplits"],
             "bandwidth_before": before["bandwidth"], "bandwidth_after": after["bandwidth"],
             "profile_before": before["profile"], "profile_after": after["profile"],
+            "heatmap": heatmap,
             "parity_vs_reference": bool(same), "parity_checker": kind,
             "cpu": {"rcm_s": t1 - t0, "permute2d_s": t2 - t1, "kind": kind, "cores": HOST_THREADS,
                     "gnnz_per_s": nnz / (t2 - t0) / 1e9}}
