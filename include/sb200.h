@@ -248,7 +248,8 @@ int sb200_csr_to_csc_block(int device, int64_t row_lo, int64_t n_local, int64_t 
 int sb200_exclusive_scan(int device, int64_t n, const void *in, void *out, int dtype,
                          void *stream);
 
-/* out_rank[i] = number of keys smaller than keys[i]; keys must be distinct and < key_bound. */
+/* out_rank[i] = position of keys[i] in the stable ascending order of the keys (equal keys are
+ * ranked by index); keys < key_bound. */
 int sb200_rank_keys(int device, int64_t n, const void *keys, int64_t key_bound, void *out_rank,
                     int id_type, void *stream);
 
@@ -278,6 +279,15 @@ int sb200_reorder_heatmap(int device, int64_t n, int64_t m, int64_t nnz, const v
                           const void *col, const void *order_r, const void *order_c,
                           int num_parts, void *out_heat, int id_type, int nnz_type,
                           int feature_type, void *stream);
+
+/* reorder::BOBAReorder::GetReorderCOO (reorder/boba_reorder.cc:35-137): out_inv[max(n, m)],
+ * inv[v] = new position of v.  The COO must be (row, col)-sorted, as format::COO's constructor
+ * leaves it.  Vertices are placed by their first appearance in the row array of the list sorted
+ * by (col, row), then by their first appearance in its column array, then by id; the sequential
+ * and the (single-threaded) parallel variant of the reference give this same order.
+ * SB200_ERR_BAD_ARG when 2 * nnz does not fit in IDType (the reference computes it in IDType). */
+int sb200_boba_reorder(int device, int64_t n, int64_t m, int64_t nnz, const void *row,
+                       const void *col, void *out_inv, int id_type, void *stream);
 
 /* ---- multi-GPU: row-block sharded operators over peer memory ----
  *

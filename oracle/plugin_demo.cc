@@ -188,6 +188,20 @@ static void run_case(const char *name, Coo c, context::CPUContext &cpu, context:
   I *g_got = dg.GetDegrees(dcsr, {&gpu}, false);
   CHECK(same(g_ref, g_got, n), "Degrees");
 
+  // ---- BOBAReorder (the reference works on the host COO; the plugin on the CUDACSR)
+  STEP("BOBAReorder");
+  {
+    reorder::BOBAReorder<I, N, V> boba(true);
+    sb200_plugin::Register(boba);
+    auto *coo_h = csr_ref->template Convert<format::COO>(&cpu);
+    I *b_ref = boba.GetReorder(coo_h, {&cpu}, false);
+    I *b_got = boba.GetReorder(dcsr, {&gpu}, false);
+    CHECK(same(b_ref, b_got, n), "BOBAReorder");
+    delete[] b_ref;
+    delete[] b_got;
+    delete coo_h;
+  }
+
   // ---- ReorderHeatmap (rows and columns renumbered by the RCM permutation)
   STEP("ReorderHeatmap");
   {

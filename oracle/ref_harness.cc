@@ -52,6 +52,8 @@ void operator delete[](void *p, std::size_t) noexcept { std::free(p); }
 
 #include <unistd.h>
 
+#include <omp.h>
+
 #include <any>
 #include <cstdint>
 #include <cstdio>
@@ -74,6 +76,7 @@ void operator delete[](void *p, std::size_t) noexcept { std::free(p); }
 #include "sparsebase/format/csc.h"
 #include "sparsebase/format/csr.h"
 #include "sparsebase/io/edge_list_reader.h"
+#include "sparsebase/reorder/boba_reorder.h"
 #include "sparsebase/reorder/degree_reorder.h"
 #include "sparsebase/reorder/rcm_reorder.h"
 #include "sparsebase/reorder/reorder_heatmap.h"
@@ -254,6 +257,22 @@ int degree_distribution(int64_t n, int64_t m, N *row_ptr, I *col, V *vals, F *o_
   return 0;
 }
 
+// reorder::BOBAReorder (reorder/boba_reorder.cc:35-137); sequential != 0 selects the sequential
+// variant (the parallel one updates its minima in an OpenMP loop without atomics: the harness
+// runs it with one thread).
+template <typename I, typename N, typename V>
+int boba_reorder(int64_t n, int64_t m, int64_t nnz, I *row, I *col, int sequential, I *out_inv) {
+  format::COO<I, N, V> coo((I)n, (I)m, (N)nnz, row, col, (V *)nullptr, format::kNotOwned, true);
+  reorder::BOBAReorder<I, N, V> op(sequential != 0);
+  const int threads = omp_get_max_threads();
+  if (!sequential) omp_set_num_threads(1);
+  I *inv = op.GetReorder(&coo, {&g_cpu}, true);
+  if (!sequential) omp_set_num_threads(threads);
+  copy_out(out_inv, inv, (size_t)(n >= m ? n : m));
+  delete[] inv;
+  return 0;
+}
+
 // reorder::ReorderHeatmap (reorder/reorder_heatmap.cc:43-120) with num_parts = b.  Returns 1
 // where the reference throws (b larger than a dimension).
 template <typename I, typename N, typename V, typename F>
@@ -412,6 +431,10 @@ int edges_to_coo(int64_t n_edges, I *u, I *v, V *w, int remove_duplicates, int r
                                   void *odist, int64_t *out4, void *oavg) {                  \
     return degree_features<I, N, V, F>(n, m, (N *)rp, (I *)col, (I *)odeg, (F *)odist, out4, \
                                        (F *)oavg);                                           \
+  }                                                                                          \
+  int sbref_boba_reorder_##TAG(int64_t n, int64_t m, int64_t nnz, void *row, void *col,      \
+                               int sequential, void *oinv) {                                 \
+    return boba_reorder<I, N, V>(n, m, nnz, (I *)row, (I *)col, sequential, (I *)oinv);      \
   }                                                                                          \
   int sbref_reorder_heatmap_##TAG(int64_t n, int64_t m, void *rp, void *col, void *pr,       \
                                   void *pc, int b, void *oheat) {                            \

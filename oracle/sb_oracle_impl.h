@@ -537,6 +537,51 @@ int FN(degree_features)(int64_t n, int64_t m, void *rp_, void *col_, void *odeg_
   return 0;
 }
 
+/* reorder/boba_reorder.cc:35-137 -- BOBAReorder::GetReorderCOO.  The list is sorted by
+ * (col, row) (:63-66); the sequential variant (:73-105) places a vertex at its first appearance
+ * in the row array of the sorted list, then (vertices never seen there) at its first appearance
+ * in the column array, then the vertices without entries by id; the parallel variant (:107-127)
+ * states the same order as key[v] = min index of v in rows ++ cols (2 * nnz if absent), ranked
+ * by (key, id) -- restated here in that form (its OpenMP loop updates the minimum without
+ * atomics; single-threaded it is this).  inv[v] = new position of v, nodes = max(n, m). */
+static int FN(boba_cmp)(const void *a_, const void *b_) {
+  const I *a = (const I *)a_, *b = (const I *)b_;
+  if (a[1] != b[1]) return a[1] < b[1] ? -1 : 1;
+  if (a[0] != b[0]) return a[0] < b[0] ? -1 : 1;
+  return 0;
+}
+static int FN(boba_key_cmp)(const void *a_, const void *b_) {
+  const int64_t *a = (const int64_t *)a_, *b = (const int64_t *)b_;
+  if (a[0] != b[0]) return a[0] < b[0] ? -1 : 1;
+  if (a[1] != b[1]) return a[1] < b[1] ? -1 : 1;
+  return 0;
+}
+int FN(boba_reorder)(int64_t n, int64_t m, int64_t nnz, void *row_, void *col_, void *out_inv_) {
+  const I *row = (const I *)row_, *col = (const I *)col_;
+  I *inv = (I *)out_inv_;
+  const int64_t nodes = n >= m ? n : m;
+  I *pairs = (I *)malloc(sizeof(I) * 2 * (size_t)(nnz > 0 ? nnz : 1));
+  for (int64_t i = 0; i < nnz; i++) {
+    pairs[2 * i] = row[i];
+    pairs[2 * i + 1] = col[i];
+  }
+  qsort(pairs, (size_t)nnz, 2 * sizeof(I), FN(boba_cmp));
+  int64_t *key = (int64_t *)malloc(sizeof(int64_t) * 2 * (size_t)(nodes > 0 ? nodes : 1));
+  for (int64_t v = 0; v < nodes; v++) {
+    key[2 * v] = 2 * nnz;
+    key[2 * v + 1] = v;
+  }
+  for (int64_t i = 0; i < nnz; i++)
+    if (i < key[2 * (int64_t)pairs[2 * i]]) key[2 * (int64_t)pairs[2 * i]] = i;
+  for (int64_t i = 0; i < nnz; i++)
+    if (nnz + i < key[2 * (int64_t)pairs[2 * i + 1]]) key[2 * (int64_t)pairs[2 * i + 1]] = nnz + i;
+  qsort(key, (size_t)nodes, 2 * sizeof(int64_t), FN(boba_key_cmp));
+  for (int64_t i = 0; i < nodes; i++) inv[key[2 * i + 1]] = (I)i;
+  free(key);
+  free(pairs);
+  return 0;
+}
+
 /* reorder/reorder_heatmap.cc:43-120 -- ReorderHeatmapCSRArrayArray: the b x b grid of nonzero
  * densities of the matrix as it would look after the row / column permutations (order[i] = new
  * position of i): bsize = n / b for BOTH dimensions (:62), block index clamped to b - 1

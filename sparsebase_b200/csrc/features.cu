@@ -283,6 +283,32 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------ BOBAReorder
+// reorder/boba_reorder.cc:35-137: the COO is sorted by (col, row); a vertex is placed by its
+// first appearance in the row array of that list, then -- if it never appears there -- by its
+// first appearance in the column array, then by id (vertices without entries).  The parallel
+// variant of the reference states it as a key: key[v] = min index of v in rows ++ cols
+// (:107-118), never-seen vertices keep 2 * nnz, and vertices are ranked by (key, id) (:120-127);
+// the sequential variant (:73-105) produces the same order.
+template <typename SI, typename UI>
+__global__ void boba_first_kernel(const UI *__restrict__ rows_sorted,
+                                  const UI *__restrict__ cols_sorted, int64_t nnz,
+                                  SI *__restrict__ key) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const UI r = rows_sorted[p], c = cols_sorted[p];
+    // (consecutive entries of one column are consecutive here: one atomic per run and lane
+    // would do, but a row id repeats only across columns)
+    atomicMin(&key[r], (SI)p);
+    if (p == 0 || cols_sorted[p - 1] != c) atomicMin(&key[c], (SI)(nnz + p));
+  }
+}
+template <typename SI>
+__global__ void boba_fill_kernel(SI *__restrict__ key, int64_t nodes, SI value) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nodes) key[i] = value;
+}
+
 // ------------------------------------------------------------------ ReorderHeatmap
 // reorder/reorder_heatmap.cc:43-120: density[bu][bv] counts the nonzeros whose permuted
 // coordinates (order_r[i], order_c[col]) fall into block (bu, bv) of a b x b grid with
@@ -506,6 +532,43 @@ int sb200_reorder_heatmap(int device, int64_t n, int64_t m, int64_t nnz, const v
         SB_LAUNCH((heatmap_finish_kernel<N, double>), (unsigned)ceil_div(cells, 256), 256, 0, st,
                   (const unsigned long long *)density, (const N *)row_ptr, n, cells,
                   (double *)out_heat);
+    });
+  });
+}
+
+int sb200_boba_reorder(int device, int64_t n, int64_t m, int64_t nnz, const void *row,
+                       const void *col, void *out_inv, int id_type, void *stream) {
+  return guarded(device, [&] {
+    const int64_t nodes = n > m ? n : m;
+    SB_REQUIRE(n >= 0 && m >= 0 && nnz >= 0 && (nodes == 0 || out_inv) && (nnz == 0 || (row && col)),
+               SB200_ERR_BAD_ARG, "bad argument");
+    if (nodes == 0) return;
+    Workspace ws(device, (cudaStream_t)stream);
+    cudaStream_t st = ws.stream();
+    dispatch_id(id_type, [&](auto I_) {
+      using I = decltype(I_);
+      using UI = typename std::make_unsigned<I>::type;
+      using SI = typename std::conditional<sizeof(I) == 4, int, long long>::type;
+      // boba_reorder.cc:44,113 computes nnzs * 2 in IDType
+      SB_REQUIRE((uint64_t)nnz * 2 + 1 < ((uint64_t)1 << (8 * sizeof(I) - 1)), SB200_ERR_BAD_ARG,
+                 "2 * nnz does not fit in IDType");
+      SI *key = reinterpret_cast<SI *>(ws.alloc<I>(nodes));
+      SB_LAUNCH((boba_fill_kernel<SI>), (unsigned)ceil_div(nodes, 256), 256, 0, st, key, nodes,
+                (SI)(2 * nnz));
+      if (nnz > 0) {
+        UI *k_out = ws.alloc<UI>(nnz), *r_out = ws.alloc<UI>(nnz);
+        UI *k_tmp = ws.alloc<UI>(nnz), *r_tmp = ws.alloc<UI>(nnz);
+        // stable sort by column of the (row, col)-sorted list = the reference's (col, row) sort
+        radix_sort<UI, UI, NoVal>(ws, {(UI *)col, (UI *)row, nullptr}, {k_out, r_out, nullptr},
+                                  {k_tmp, r_tmp, nullptr}, nnz,
+                                  {{0, bits_for((uint64_t)(nodes > 1 ? nodes - 1 : 1))}});
+        const int64_t cap = (int64_t)device_info(device).sm_count * 16;
+        const int64_t blocks = ceil_div(nnz, 256);
+        SB_LAUNCH((boba_first_kernel<SI, UI>), (unsigned)(blocks < cap ? blocks : cap), 256, 0, st,
+                  (const UI *)r_out, (const UI *)k_out, nnz, key);
+      }
+      const int rc = sb200_rank_keys(device, nodes, key, 2 * nnz + 1, out_inv, id_type, stream);
+      if (rc != SB200_OK) throw Error{rc};
     });
   });
 }

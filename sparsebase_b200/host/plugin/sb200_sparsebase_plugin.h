@@ -43,6 +43,7 @@
 #include "sparsebase/format/cuda_csr_cuda.cuh"
 #include "sparsebase/permute/permute_order_one.h"
 #include "sparsebase/permute/permute_order_two.h"
+#include "sparsebase/reorder/boba_reorder.h"
 #include "sparsebase/reorder/degree_reorder.h"
 #include "sparsebase/reorder/rcm_reorder.h"
 #include "sparsebase/reorder/reorder_heatmap.h"
@@ -415,6 +416,27 @@ I *DegreeReorderCUDACSR(std::vector<sbase::format::Format *> formats,
   return h;
 }
 
+// reorder::BOBAReorder works on a COO (reorder/boba_reorder.cc:18-21); the device format of the
+// reference is CUDACSR, so the rows are expanded on the device first (sb200_csr_to_coo).
+template <typename I, typename N, typename V>
+I *BOBAReorderCUDACSR(std::vector<sbase::format::Format *> formats, sbase::utils::Parameters *) {
+  auto *csr = formats[0]->AsAbsolute<sbase::format::CUDACSR<I, N, V>>();
+  const int dev = csr->get_cuda_context()->device_id;
+  const auto dims = csr->get_dimensions();
+  const size_t nnz = csr->get_num_nnz(), nodes = dims[0] > dims[1] ? dims[0] : dims[1];
+  I *d_row = dev_alloc<I>(dev, nnz ? nnz : 1), *d_col = dev_alloc<I>(dev, nnz ? nnz : 1);
+  I *inv = dev_alloc<I>(dev, nodes ? nodes : 1);
+  int rc = sb200_csr_to_coo(dev, dims[0], dims[1], nnz, csr->get_row_ptr(), csr->get_col(), nullptr,
+                            d_row, d_col, nullptr, dtype_of<I>(), dtype_of<N>(), SB200_VOID,
+                            nullptr);
+  if (rc == SB200_OK)
+    rc = sb200_boba_reorder(dev, dims[0], dims[1], nnz, d_row, d_col, inv, dtype_of<I>(), nullptr);
+  I *h = rc == SB200_OK ? to_host(dev, inv, nodes) : nullptr;
+  dev_free(dev, d_row), dev_free(dev, d_col), dev_free(dev, inv);
+  check(rc, dev);
+  return h;
+}
+
 template <typename I, typename N, typename V>
 I *RCMReorderCUDACSR(std::vector<sbase::format::Format *> formats, sbase::utils::Parameters *) {
   auto *csr = formats[0]->AsAbsolute<sbase::format::CUDACSR<I, N, V>>();
@@ -538,6 +560,10 @@ void Register(sbase::reorder::ReorderHeatmap<I, N, V, F> &op) {
 template <typename I, typename N, typename V>
 void Register(sbase::reorder::DegreeReorder<I, N, V> &op) {
   op.RegisterFunction({sbase::format::CUDACSR<I, N, V>::get_id_static()}, DegreeReorderCUDACSR<I, N, V>);
+}
+template <typename I, typename N, typename V>
+void Register(sbase::reorder::BOBAReorder<I, N, V> &op) {
+  op.RegisterFunction({sbase::format::CUDACSR<I, N, V>::get_id_static()}, BOBAReorderCUDACSR<I, N, V>);
 }
 template <typename I, typename N, typename V>
 void Register(sbase::reorder::RCMReorder<I, N, V> &op) {

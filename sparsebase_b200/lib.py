@@ -27,7 +27,7 @@ SYMBOLS = [
     "sb200_rcm_last_resplits",
     "sb200_rcm_last_speculation", "sb200_permute2d", "sb200_permute1d",
     "sb200_inverse_permutation",
-    "sb200_degrees", "sb200_degree_distribution", "sb200_degree_features", "sb200_reorder_heatmap", "sb200_edges_to_coo", "sb200_partition_rows", "sb200_launch_count",
+    "sb200_degrees", "sb200_degree_distribution", "sb200_degree_features", "sb200_reorder_heatmap", "sb200_boba_reorder", "sb200_edges_to_coo", "sb200_partition_rows", "sb200_launch_count",
     "sb200_reset_launch_count", "sb200_coo_to_csr_block", "sb200_csr_to_csc_block",
     "sb200_exclusive_scan", "sb200_rank_keys", "sb200_max_degree", "sb200_degree_histogram",
     "sb200_degree_rank_combine",
@@ -275,6 +275,14 @@ def degree_features(n, nnz, row_ptr, col=None, id_dtype=torch.int32,
     out = dict(zip(("min_degree", "max_degree", "bandwidth", "profile"), (int(x) for x in sc)))
     out["avg_degree"] = avg.value
     return deg, dist, out
+
+
+def boba_reorder(n, m, row, col):
+    """BOBAReorder on a (row, col)-sorted device COO: inv[max(n, m)] (inv[v] = new position)."""
+    inv = torch.empty(max(n, m), dtype=row.dtype, device=row.device)
+    _check(load().sb200_boba_reorder(_dev(row), _i64(n), _i64(m), _i64(row.numel()), _p(row),
+                                     _p(col), _p(inv), _DT[row.dtype], _stream(row)))
+    return inv
 
 
 def reorder_heatmap(n, m, row_ptr, col, order_r, order_c, num_parts=3,

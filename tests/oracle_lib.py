@@ -213,6 +213,23 @@ class Oracle:
         return deg, dist, dict(zip(("min_degree", "max_degree", "bandwidth", "profile"),
                                    (int(x) for x in sc))), avg[0]
 
+    def boba_reorder(self, n, m, row, col, sequential=True, nnz_dtype=np.int32,
+                     vals_dtype=np.float32):
+        """BOBAReorder on a COO: inv[max(n, m)] (`sequential` only selects the reference's
+        variant; the restatement has one form)."""
+        row, col = _c(row), _c(col)
+        t = tag_of(row.dtype, nnz_dtype, vals_dtype)
+        out = np.empty(max(n, m), row.dtype)
+        if self.prefix == "sbref":
+            rc = self._fn(f"boba_reorder_{t}")(self._i64(n), self._i64(m), self._i64(len(row)),
+                                               _ptr(row), _ptr(col), ctypes.c_int(int(sequential)),
+                                               _ptr(out))
+        else:
+            rc = self._fn(f"boba_reorder_{t}")(self._i64(n), self._i64(m), self._i64(len(row)),
+                                               _ptr(row), _ptr(col), _ptr(out))
+        assert rc == 0
+        return out
+
     def reorder_heatmap(self, n, row_ptr, col, order_r, order_c, num_parts,
                         vals_dtype=np.float32):
         """ReorderHeatmap: the num_parts x num_parts density grid (FeatureType of the type set),

@@ -4,6 +4,7 @@
 * fused degree features + Bandwidth + Profile   feature/degrees_degree_distribution.cc:147-166,
   feature/min_max_avg_degree.cc:168-191, feature/bandwidth.cc:92-111, feature/profile.cc:92-106
 * ReorderHeatmap (rank 3)   reorder/reorder_heatmap.cc:43-120
+* BOBAReorder (rank 4)   reorder/boba_reorder.cc:35-137
 
 CPU part: the restated oracle against the compiled reference (the reference's EdgeListReader
 reads a text file the harness writes) and against the reference's own golden vectors
@@ -118,6 +119,37 @@ def test_degree_features_reference_goldens():
 
 
 # ------------------------------------------------------------------ GPU
+def boba_cases():
+    """(name, n, m, row, col): (row, col)-sorted, unique COO lists -- symmetric graphs, and an
+    asymmetric one with vertices that only appear as columns and vertices without entries."""
+    out = []
+    n, r, c = graphs.rmat(10, 8, seed=3)
+    out.append(("rmat10", n, n, r, c))
+    n, r, c = graphs.band(3000, 15, 0.5, seed=9, shuffle_seed=10)
+    out.append(("band3k_shuffled", n, n, r, c))
+    n, r, c = graphs.multi_component()
+    out.append(("multi", n, n, r, c))
+    rng = np.random.default_rng(5)
+    key = np.unique(rng.integers(0, 200, 2000).astype(np.int64) * 500 + rng.integers(150, 450, 2000))
+    out.append(("asym", 500, 500, key // 500, key % 500))
+    return out
+
+
+@needs_ref
+def test_boba_restated_equals_reference():
+    """Both variants of the reference (the parallel one run with one thread: its OpenMP loop
+    updates the minima without atomics)."""
+    orc, ref = oracle_lib.restated(), oracle_lib.reference()
+    for name, n, m, row, col in boba_cases():
+        for idt, nt, vt in ((np.int32, np.int32, np.float32), (np.int64, np.int64, np.float64)):
+            r2, c2 = row.astype(idt), col.astype(idt)
+            a = orc.boba_reorder(n, m, r2, c2, nnz_dtype=nt, vals_dtype=vt)
+            assert sorted(a.tolist()) == list(range(max(n, m))), name
+            for seq in (True, False):
+                e = ref.boba_reorder(n, m, r2, c2, sequential=seq, nnz_dtype=nt, vals_dtype=vt)
+                assert eq(a, e), (name, idt, seq)
+
+
 HEAT_PARTS = (1, 2, 3, 7, 64, 100)
 
 
@@ -251,3 +283,18 @@ def test_reorder_heatmap_gpu(sb):
     rp, pr = graphs.csr_of(n, r, c), sb.degree_reorder(n, dev(graphs.csr_of(n, r, c)), True)
     exp = orc.reorder_heatmap(n, rp, c, host(pr), host(pr), 16)
     assert eq(host(sb.reorder_heatmap(n, n, dev(rp), dev(c), pr, pr, 16)), exp)
+
+
+@pytest.mark.gpu
+def test_boba_reorder_gpu(sb):
+    orc = oracle_lib.restated()
+    cases = boba_cases()
+    n, r, c = graphs.rmat(15, 8, seed=21)
+    cases.append(("rmat15", n, n, r, c))
+    cases.append(("empty", 7, 7, np.zeros(0, np.int64), np.zeros(0, np.int64)))
+    for name, n, m, row, col in cases:
+        for idt, nt, vt in ((np.int32, np.int32, np.float32), (np.int64, np.int64, np.float64)):
+            r2, c2 = row.astype(idt), col.astype(idt)
+            exp = orc.boba_reorder(n, m, r2, c2, nnz_dtype=nt, vals_dtype=vt)
+            got = sb.boba_reorder(n, m, dev(r2), dev(c2))
+            assert eq(host(got), exp), (name, idt)
