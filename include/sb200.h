@@ -307,7 +307,12 @@ int sb200_boba_reorder(int device, int64_t n, int64_t m, int64_t nnz, const void
  *                           with whatever the application uses (MPI, torch.distributed ...),
  *                           sb200_mg_comm_connect
  *   one process, ndev GPUs  sb200_mg_comm_create_local: ndev connected communicators; call the
- *                           operators from one host thread per GPU (sb200_mg_run_ranks)
+ *                           operators from one host thread per GPU (sb200_mg_run_ranks), every
+ *                           rank on its own stream.  Several ranks may share a device (tests):
+ *                           that needs non-blocking streams, no cudaMalloc / cudaFree between
+ *                           collective calls, and CUDA_MODULE_LOADING=EAGER (a lazily loaded
+ *                           kernel synchronises the context on its first launch and would wait
+ *                           for the other rank's barrier kernel)
  */
 typedef struct sb200_mg_comm sb200_mg_comm_t;
 int sb200_mg_comm_create(int device, int rank, int world, size_t window_bytes,

@@ -131,3 +131,38 @@ def test_peer_memory_single_rank(sb):
     x = dev(graphs.vals_for(n, seed=4))
     assert torch.equal(mg.permute1d(comm, [0, n], x, inv), sb.permute1d(x, inv))
     comm.destroy()
+
+
+def build_mg_local_test():
+    src = os.path.join(ROOT, "tests", "cpp", "mg_local_test.cc")
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "mg_local_test")
+    lib = os.path.join(ROOT, "sparsebase_b200", "libsb200.so")
+    deps = [src, os.path.join(ROOT, "include", "sb200.h"), lib]
+    if os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps):
+        return exe
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", f"-I{os.path.join(ROOT, 'include')}",
+           f"-I{cuda}/include", src, "-o", exe, f"-L{os.path.join(ROOT, 'sparsebase_b200')}",
+           "-lsb200", f"-L{cuda}/lib64", "-lcudart", "-lpthread",
+           "-Wl,-rpath,$ORIGIN/../../../sparsebase_b200"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    return exe
+
+
+@pytest.mark.parametrize("ranks,log2n", [(2, 14)])
+def test_single_process_ranks_through_the_c_abi(ranks, log2n):
+    """sb200_mg_comm_create_local + sb200_mg_run_ranks from a C++ program (no torch, one process):
+    every sharded operator against the single-GPU one, one rank per GPU."""
+    if torch.cuda.device_count() < ranks:
+        pytest.skip("one GPU per rank (ranks sharing a device: barriers work with eager module "
+                    "loading, but DegreeReorder mismatched on the one attempt -- not supported)")
+    exe = build_mg_local_test()
+    # ranks that SHARE a device need eager module loading: with CUDA's lazy loading the first
+    # launch of a kernel synchronises the context, i.e. waits for the other rank's barrier
+    # kernel, which is waiting for this rank (the documented lazy-loading deadlock)
+    env = dict(os.environ, CUDA_MODULE_LOADING="EAGER")
+    r = subprocess.run([exe, str(ranks), str(log2n)], capture_output=True, text=True, timeout=600,
+                       env=env)
+    assert r.returncode == 0 and "MG LOCAL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
