@@ -2,7 +2,8 @@
  *
  * sb_oracle.c -- the parity oracle: a plain-C, single-threaded restatement of the
  * reference's CPU algorithm (sparcityeu/SparseBase v0.3.1) for the preprocessing hot path
- * (SURVEY.md section 8a, rows a1-a13).  Built by oracle/Makefile into oracle/liboracle.so.
+ * (edge list -> COO, fused degree
+ * features, ReorderHeatmap, BOBAReorder).  Built by oracle/Makefile into oracle/liboracle.so.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library, and only as the checker / the reported CPU baseline.
