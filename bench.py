@@ -644,7 +644,8 @@ def main():
                      "kernel": "Permute2D gather / renumber / row-sort kernels (ss_tile_kernel + "
                                "segmented long-row sort) -- the dominant operator of the step",
                      "achieved": p2d["alg_gb_per_s"] / world, "peak": peak, "unit": "GB/s",
-                     "frac": p2d["roofline_frac"], "traffic": ncu_traffic(),
+                     "frac": p2d["roofline_frac"],
+                     "traffic": ncu_traffic() if world == 1 else None,  # (captured on one GPU)
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALG_BYTES["permute2d"](n, nnz) // world,
                      "note": "achieved is per GPU: algorithmic bytes of Permute2D / N / its time"},
