@@ -42,7 +42,35 @@ def main():
             degree_desc=ref.degree_reorder(n, rp, cc, False), rcm=rcm, p2d_row_ptr=p2d[0],
             p2d_col=p2d[1], p2d_vals=p2d[2], csc_col_ptr=csc[0], csc_row=csc[1], csc_vals=csc[2],
             degree_distribution=ref.degree_distribution(n, rp, cc))
+        # the callers either side of the path: fused features, heatmaps under two
+        # orders, BOBA
+        fdeg, fdist, fsc, favg = ref.degree_features(n, rp, cc)
+        deg_asc = ref.degree_reorder(n, rp, cc, True)
+        np.savez_compressed(
+            os.path.join(HERE, f"ref_features_{name}.npz"), n=n, row_ptr=rp, col=cc,
+            coo_row=row, coo_col=col, degrees=fdeg, dist=fdist,
+            scalars=np.array([fsc[k] for k in ("min_degree", "max_degree", "bandwidth", "profile")],
+                             np.int64),
+            avg=np.array([favg]), rcm=rcm, degree_asc=deg_asc,
+            heat_rcm_5=ref.reorder_heatmap(n, rp, cc, rcm, rcm, 5),
+            heat_degree_3=ref.reorder_heatmap(n, rp, cc, deg_asc, deg_asc, 3),
+            heat_identity_16=ref.reorder_heatmap(n, rp, cc, np.arange(n, dtype=np.int32),
+                                                 np.arange(n, dtype=np.int32), 16),
+            boba=ref.boba_reorder(n, n, row, col, sequential=True))
         print(name, n, len(row))
+    # an edge list through EdgeListReader::ReadCOO (weights a function of the unordered pair)
+    rng = np.random.default_rng(107)
+    u = rng.integers(0, 300, 4000).astype(np.int32)
+    v = rng.integers(0, 300, 4000).astype(np.int32)
+    lo, hi = np.minimum(u, v).astype(np.int64), np.maximum(u, v).astype(np.int64)
+    w = (((lo * 2654435761 + hi * 40503) % 4096).astype(np.float32) - 2048.0) * 0.5
+    out = {"u": u, "v": v, "w": w}
+    for tag, flags in (("dedup", (True, False, False, False)), ("sym", (True, True, True, False)),
+                       ("square", (False, True, False, True))):
+        en, em, er, ec, evv = ref.edges_to_coo(u, v, w, *flags)
+        out.update({f"{tag}_dims": np.array([en, em], np.int64), f"{tag}_row": er, f"{tag}_col": ec,
+                    f"{tag}_vals": evv})
+    np.savez_compressed(os.path.join(HERE, "ref_edge_list.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -188,6 +188,38 @@ def test_reorder_heatmap_restated_equals_reference():
                 assert eq(a, e), (name, idt, b)
 
 
+FEATURE_FIXTURES = ("rmat9", "poisson24x17", "band600", "multi")
+
+
+@pytest.mark.parametrize("name", FEATURE_FIXTURES)
+def test_restated_equals_committed_reference_fixtures(name):
+    """tests/golden/ref_features_*.npz were written by the compiled reference
+    (tests/golden/make_golden.py): the restatement must reproduce them where the reference tree
+    is not mounted, too."""
+    orc = oracle_lib.restated()
+    f = np.load(os.path.join(HERE, "golden", f"ref_features_{name}.npz"))
+    n, rp, col = int(f["n"]), f["row_ptr"], f["col"]
+    deg, dist, sc, avg = orc.degree_features(n, rp, col)
+    assert eq(deg, f["degrees"]) and eq(dist, f["dist"])
+    assert [sc[k] for k in ("min_degree", "max_degree", "bandwidth", "profile")] == list(f["scalars"])
+    assert np.float32(avg).tobytes() == f["avg"].astype(np.float32).tobytes()
+    ident = np.arange(n, dtype=np.int32)
+    assert eq(orc.reorder_heatmap(n, rp, col, f["rcm"], f["rcm"], 5), f["heat_rcm_5"])
+    assert eq(orc.reorder_heatmap(n, rp, col, f["degree_asc"], f["degree_asc"], 3), f["heat_degree_3"])
+    assert eq(orc.reorder_heatmap(n, rp, col, ident, ident, 16), f["heat_identity_16"])
+    assert eq(orc.boba_reorder(n, n, f["coo_row"], f["coo_col"]), f["boba"])
+
+
+def test_restated_edge_list_equals_committed_reference_fixture():
+    orc = oracle_lib.restated()
+    f = np.load(os.path.join(HERE, "golden", "ref_edge_list.npz"))
+    for tag, flags in (("dedup", (True, False, False, False)), ("sym", (True, True, True, False)),
+                       ("square", (False, True, False, True))):
+        n, m, r, c, v = orc.edges_to_coo(f["u"], f["v"], f["w"], *flags)
+        assert [n, m] == list(f[f"{tag}_dims"]), tag
+        assert eq(r, f[f"{tag}_row"]) and eq(c, f[f"{tag}_col"]) and eq(v, f[f"{tag}_vals"]), tag
+
+
 @pytest.fixture(scope="module")
 def sb():
     from sparsebase_b200 import lib
